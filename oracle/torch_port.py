@@ -1,0 +1,154 @@
+"""CPU oracle (TEST INFRASTRUCTURE, not product code) -- a dense, eager PyTorch
+restatement of the reference's own algorithm for the hot path.
+
+This is the "port" that ``bench.py`` times as ``cpu_baseline`` / ``--impl
+reference``: it does what the reference does, the way the reference does it --
+materialise the (N points x M nodes) tensors, apply the kernel, read out with a
+linear layer, differentiate with three nested ``torch.autograd.grad`` calls and
+back-propagate through that graph -- so its cost is the reference's cost.
+
+Followed reference code (relative to /root/reference):
+  shift/scale      code/spinn2d.py:130-135 (multiply by 1/h), code/spinn1d.py:110-112 (divide by h)
+  kernels          code/spinn2d.py:191-205, code/spinn1d.py:176-189
+  read-out         code/spinn2d.py:169-179, code/spinn1d.py:147-156
+  jets             code/pde2d_base.py:46-62, code/ode_base.py:32-42
+  backward         code/common.py:242-248
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` may import this.
+Pinned against reference-generated fixtures by ``tests/test_oracle_golden.py``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.autograd as ag
+import torch.nn.functional as F
+
+
+def _hat_constants(dim, dtype, device):
+    # fp32 tensors in the reference (code/spinn2d.py:198-199); cast afterwards.
+    k = torch.tensor([1.0 + 2.0 * dim * np.log(2.0)], dtype=torch.float32)
+    fac = F.softplus(torch.tensor([1.0], dtype=torch.float32))
+    return k.to(device=device, dtype=dtype), fac.to(device=device, dtype=dtype)
+
+
+def _kernel(kind, *hs):
+    if kind in ("gaussian", 0):
+        s = hs[0] * hs[0]
+        for t in hs[1:]:
+            s = s + t * t
+        return torch.exp(-0.5 * s)
+    k, fac = _hat_constants(len(hs), hs[0].dtype, hs[0].device)
+    z = k
+    for t in hs:
+        z = z - F.softplus(2.0 * t) - F.softplus(-2.0 * t)
+    return F.softplus(z) / fac
+
+
+def forward2d(kind, x, y, xc, yc, h, W, b):
+    """(N,) x2, (M,) x3, (K,M), (K,)|None -> (N,K)"""
+    fac = 1.0 / h
+    xh = (x.unsqueeze(1) - xc) * fac
+    yh = (y.unsqueeze(1) - yc) * fac
+    return F.linear(_kernel(kind, xh, yh), W, b)
+
+
+def forward1d(kind, x, xc, h, W, b):
+    return F.linear(_kernel(kind, (x.unsqueeze(1) - xc) / h), W, b)
+
+
+def _d(u, inputs):
+    return ag.grad(u, inputs, grad_outputs=torch.ones_like(u),
+                   retain_graph=True, create_graph=True)
+
+
+def jets2d(kind, x, y, xc, yc, h, W, b):
+    """x, y must require grad.  Returns list over k of (u,ux,uy,uxx,uyy,uxy)."""
+    U = forward2d(kind, x, y, xc, yc, h, W, b)
+    out = []
+    for k in range(U.shape[1]):
+        u = U[:, k]
+        ux, uy = _d(u, (x, y))
+        uxx, uxy = _d(ux, (x, y))
+        _, uyy = _d(uy, (x, y))
+        out.append((u, ux, uy, uxx, uyy, uxy))
+    return out
+
+
+def jets1d(kind, x, xc, h, W, b):
+    U = forward1d(kind, x, xc, h, W, b)
+    out = []
+    for k in range(U.shape[1]):
+        u = U[:, k]
+        (ux,) = _d(u, (x,))
+        (uxx,) = _d(ux, (x,))
+        out.append((u, ux, uxx))
+    return out
+
+
+def jets_and_grads2d(kind, x, y, xf, yf, xfix, yfix, h, W, b, gjets, dtype=torch.float32):
+    """Reference-style evaluation of jets and of the parameter gradients of
+    ``L = sum g*J``.  All inputs array-like; xf/yf are the free centres,
+    xfix/yfix the fixed ones; gjets (5|6, N, K).  Returns numpy dict."""
+    t = lambda a, rg=False: torch.tensor(np.asarray(a), dtype=dtype).requires_grad_(rg)
+    x, y = t(x, True), t(y, True)
+    xf, yf, h, W = t(xf, True), t(yf, True), t(h, True), t(W, True)
+    b = None if b is None else t(b, True)
+    xc = torch.cat((xf, t(xfix)))
+    yc = torch.cat((yf, t(yfix)))
+    g = torch.tensor(np.asarray(gjets), dtype=dtype)
+    J = jets2d(kind, x, y, xc, yc, h, W, b)
+    L = 0.0
+    for k, jk in enumerate(J):
+        for a in range(g.shape[0]):
+            L = L + (g[a, :, k] * jk[a]).sum()
+    params = [xf, yf, h, W] + ([] if b is None else [b])
+    grads = ag.grad(L, params, allow_unused=True)
+    jets = torch.stack([torch.stack(jk, 0) for jk in J], -1)      # (6, N, K)
+    out = {"jets": jets.detach().numpy(), "d_xc": grads[0].numpy(), "d_yc": grads[1].numpy(),
+           "d_h": grads[2].numpy().reshape(-1), "d_W": grads[3].numpy()}
+    if b is not None:
+        out["d_b"] = grads[4].numpy()
+    return out
+
+
+def jets_and_grads1d(kind, x, xf, xfix, h, W, b, gjets, dtype=torch.float32):
+    t = lambda a, rg=False: torch.tensor(np.asarray(a), dtype=dtype).requires_grad_(rg)
+    x = t(x, True)
+    xf, h, W = t(xf, True), t(h, True), t(W, True)
+    b = None if b is None else t(b, True)
+    xc = torch.cat((xf, t(xfix)))
+    g = torch.tensor(np.asarray(gjets), dtype=dtype)
+    J = jets1d(kind, x, xc, h, W, b)
+    L = 0.0
+    for k, jk in enumerate(J):
+        for a in range(3):
+            L = L + (g[a, :, k] * jk[a]).sum()
+    params = [xf, h, W] + ([] if b is None else [b])
+    grads = ag.grad(L, params, allow_unused=True)
+    jets = torch.stack([torch.stack(jk, 0) for jk in J], -1)
+    out = {"jets": jets.detach().numpy(), "d_xc": grads[0].numpy(),
+           "d_h": grads[1].numpy().reshape(-1), "d_W": grads[2].numpy()}
+    if b is not None:
+        out["d_b"] = grads[3].numpy()
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# the timed leg: one interior fwd+bwd of the scaled Poisson2D residual on a
+# chunk of points (code/pde2d_base.py:132-141 + code/poisson2d_sine.py:16-18)
+# --------------------------------------------------------------------------- #
+def poisson_interior_step(kind, x, y, xc, yc, h, W, b, n_total):
+    """x, y: leaf fp32 tensors with requires_grad (as code/pde2d_base.py:91);
+    xc.. W, b: leaf parameters.  Accumulates .grad like ``loss.backward()`` and
+    returns the chunk's contribution to ``(res**2).mean()``."""
+    U = forward2d(kind, x, y, xc, yc, h, W, b)
+    u = U.squeeze()
+    ux, uy = _d(u, (x, y))
+    uxx, _ = _d(ux, (x, y))
+    _, uyy = _d(uy, (x, y))
+    f = 20 * np.pi ** 2 * torch.sin(2 * np.pi * x) * torch.sin(4 * np.pi * y)
+    res = 0.1 * (uxx + uyy + f)
+    loss = (res ** 2).sum() / n_total
+    loss.backward()
+    return float(loss.detach())

@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by EXECUTING THE REFERENCE.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes
+are committed and are what travels to the GPU box.  Nothing in tests/, smoke()
+or bench.py imports this file or reads /root/reference at run time.
+
+    python tests/golden/make_golden.py            # regenerate everything
+
+What it records
+  op_*.npz     op-level: reference SPINN1D/SPINN2D (code/spinn1d.py, code/spinn2d.py)
+               with seeded, perturbed parameters -> nn(x[,y]) -> the reference's
+               own _compute_derivatives (code/pde2d_base.py:46-62, code/ode_base.py:32-42)
+               -> L = sum g*J -> autograd parameter gradients, in fp32 (the
+               reference's arithmetic) and in fp64 (same graph, cast by hand).
+  traj_*.npz   trajectory-level: the four BASELINE configs driven through the
+               reference's App.run for a few hundred Adam steps: loss history,
+               final parameters, final error norms.
+  mesh_data.npz  the irregular-domain point sets of code/mesh_data/*.dat.
+  constants.npz  SoftPlus.k / SoftPlus.fac as the reference builds them.
+"""
+import io
+import os
+import sys
+import types
+import contextlib
+
+import numpy as np
+import torch
+import torch.autograd as ag
+
+REF = "/root/reference/code"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference():
+    """matplotlib / mayavi are not installed here; the reference imports them
+    at module top level (code/spinn1d.py:4, code/spinn2d.py:3) -> empty stubs."""
+    for name in ("matplotlib", "matplotlib.pyplot", "mayavi", "mayavi.mlab"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["mayavi"].mlab = sys.modules["mayavi.mlab"]
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+class StubPDE:
+    def __init__(self, nodes, fixed, k):
+        self._n, self._f, self._k = nodes, fixed, k
+
+    def nodes(self):
+        return self._n
+
+    def fixed_nodes(self):
+        return self._f
+
+    def n_vars(self):
+        return self._k
+
+
+def _to_double(nn, act):
+    """.double() does not touch plain-attribute tensors."""
+    nn = nn.double()
+    l1 = nn.layer1
+    for name in ("xf", "yf", "fixed"):
+        if hasattr(l1, name):
+            setattr(l1, name, getattr(l1, name).double())
+    if hasattr(act, "k"):
+        act.k = act.k.double()
+        act.fac = act.fac.double()
+    return nn
+
+
+def _perturb(nn, gen, dim):
+    """zero-initialised weights make centre/width gradients vanish -> perturb."""
+    l1, l2 = nn.layer1, nn.layer2
+    with torch.no_grad():
+        l2.weight.copy_(0.3 * torch.randn(l2.weight.shape, generator=gen))
+        if l2.bias is not None:
+            l2.bias.copy_(0.1 * torch.randn(l2.bias.shape, generator=gen))
+        l1.h.mul_(1.0 + 0.3 * torch.rand(l1.h.shape, generator=gen))
+        if dim == 2:
+            l1.x.add_(0.01 * torch.randn(l1.x.shape, generator=gen))
+            l1.y.add_(0.01 * torch.randn(l1.y.shape, generator=gen))
+        else:
+            l1.center.add_(0.01 * torch.randn(l1.center.shape, generator=gen))
+
+
+def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=1.0):
+    import spinn2d
+    import pde2d_base
+    gen = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    g1 = np.linspace(lo + 0.05, hi - 0.05, n_side)
+    xn, yn = (a.ravel() for a in np.meshgrid(g1, g1, indexing="ij"))
+    if nb:
+        e = np.linspace(lo, hi, nb)
+        o = np.ones_like(e)
+        fx = np.hstack((e, hi * o, e, lo * o))
+        fy = np.hstack((lo * o, e, hi * o, e))
+        fixed = (fx, fy)
+    else:
+        fixed = ([], [])
+    xs = (lo + (hi - lo) * rs.rand(npts)).astype(np.float32)
+    ys = (lo + (hi - lo) * rs.rand(npts)).astype(np.float32)
+    gj = rs.randn(6, npts, K).astype(np.float32)
+    gj[5] = 0.0  # the reference never consumes u_xy
+    out = {"kind": kind, "K": K, "dim": 2}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        act = spinn2d.gaussian if kind == "gaussian" else spinn2d.SoftPlus()
+        nn = spinn2d.SPINN2D(StubPDE((xn, yn), fixed, K), act, fixed_h=fixed_h)
+        _perturb(nn, torch.Generator().manual_seed(seed + 1), 2)
+        if tag == "f32":
+            out.update(
+                x=xs, y=ys, gjets=gj,
+                xf=nn.layer1.x.detach().numpy().copy(), yf=nn.layer1.y.detach().numpy().copy(),
+                xfix=nn.layer1.xf.numpy().copy(), yfix=nn.layer1.yf.numpy().copy(),
+                h=nn.layer1.h.detach().numpy().reshape(-1).copy(),
+                W=nn.layer2.weight.detach().numpy().copy(), b=nn.layer2.bias.detach().numpy().copy(),
+            )
+        else:
+            nn = _to_double(nn, act)
+        x = torch.tensor(xs, dtype=dt, requires_grad=True)
+        y = torch.tensor(ys, dtype=dt, requires_grad=True)
+        U = nn(x, y)
+        U2 = U.reshape(npts, K)
+        jets = []
+        for k in range(K):
+            u = U2[:, k]
+            # the reference routine, verbatim call (it is self-free)
+            u_, ux, uy, uxx, uyy = pde2d_base.RegularPDE._compute_derivatives(None, u, x, y)
+            uxy = ag.grad(ux, y, torch.ones_like(ux), retain_graph=True, create_graph=True)[0]
+            jets.append(torch.stack((u_, ux, uy, uxx, uyy, uxy)))
+        J = torch.stack(jets, -1)                                   # (6, N, K)
+        L = (torch.tensor(gj, dtype=dt) * J).sum()
+        params = [nn.layer1.x, nn.layer1.y, nn.layer1.h, nn.layer2.weight, nn.layer2.bias]
+        gr = ag.grad(L, params)
+        out["jets_" + tag] = J.detach().numpy()
+        for nme, gv in zip(("d_xc", "d_yc", "d_h", "d_W", "d_b"), gr):
+            out[nme + "_" + tag] = gv.numpy().reshape(-1) if nme == "d_h" else gv.numpy()
+    np.savez_compressed(os.path.join(HERE, f"op_{name}.npz"), **out)
+    print("wrote", name)
+
+
+def op_case_1d(name, kind, n, npts, K, seed, fixed=True):
+    import spinn1d
+    import ode_base
+    rs = np.random.RandomState(seed)
+    xn = np.asarray([i / (n + 1) for i in range(1, n + 1)])
+    fx = np.array([0.0, 1.0]) if fixed else np.array([])
+    xs = rs.rand(npts).astype(np.float32)
+    gj = rs.randn(3, npts, K).astype(np.float32)
+    out = {"kind": kind, "K": K, "dim": 1}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        act = spinn1d.gaussian if kind == "gaussian" else spinn1d.SoftPlus()
+        nn = spinn1d.SPINN1D(StubPDE(xn, fx, K), act)
+        _perturb(nn, torch.Generator().manual_seed(seed + 1), 1)
+        if tag == "f32":
+            out.update(
+                x=xs, gjets=gj, xf=nn.layer1.center.detach().numpy().copy(),
+                xfix=nn.layer1.fixed.numpy().copy(), h=nn.layer1.h.detach().numpy().copy(),
+                W=nn.layer2.weight.detach().numpy().copy(), b=nn.layer2.bias.detach().numpy().copy(),
+            )
+        else:
+            nn = _to_double(nn, act)
+        x = torch.tensor(xs, dtype=dt, requires_grad=True)
+        if tag == "f64":
+            # SPINN1D.forward builds an fp32 tensor(1.0) (code/spinn1d.py:154); dividing a
+            # double tensor by a 0-dim float tensor keeps double, so no patching needed.
+            pass
+        U2 = nn(x).reshape(npts, K)
+        jets = []
+        for k in range(K):
+            u_, ux, uxx = ode_base.BasicODE._compute_derivatives(None, U2[:, k], x)
+            jets.append(torch.stack((u_, ux, uxx)))
+        J = torch.stack(jets, -1)
+        L = (torch.tensor(gj, dtype=dt) * J).sum()
+        params = [nn.layer1.center, nn.layer1.h, nn.layer2.weight, nn.layer2.bias]
+        gr = ag.grad(L, params)
+        out["jets_" + tag] = J.detach().numpy()
+        for nme, gv in zip(("d_xc", "d_h", "d_W", "d_b"), gr):
+            out[nme + "_" + tag] = gv.numpy()
+    np.savez_compressed(os.path.join(HERE, f"op_{name}.npz"), **out)
+    print("wrote", name)
+
+
+def trajectory(name, module, app_attr, args, seed=0):
+    """Drive a reference config through its own App.run for a few steps."""
+    import importlib
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    mod = importlib.import_module(module)
+    app = app_attr(mod)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        app.run(args=args)
+    sd = {k: v.detach().cpu().numpy() for k, v in app.nn.state_dict().items()}
+    err = app.plotter.get_error()
+    out = {"loss": np.asarray(app.solver.loss, dtype=np.float64),
+           "errors": np.asarray(err, dtype=np.float64),
+           "args": np.asarray(args)}
+    out.update({"sd_" + k: v for k, v in sd.items()})
+    np.savez_compressed(os.path.join(HERE, f"traj_{name}.npz"), **out)
+    print("wrote traj", name, "final loss", app.solver.loss[-1], "err", err)
+
+
+def mesh_data():
+    out = {}
+    for f in ("interior_nodes", "boundary_nodes", "interior_samples", "boundary_samples"):
+        with open(os.path.join(REF, "mesh_data", f + ".dat")) as fh:
+            n = int(fh.readline().split()[0])
+            rows = [fh.readline().split()[:2] for _ in range(n)]
+        out[f] = np.asarray(rows, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "mesh_data.npz"), **out)
+    print("wrote mesh_data", {k: v.shape for k, v in out.items()})
+
+
+def constants():
+    import spinn1d
+    import spinn2d
+    a1, a2 = spinn1d.SoftPlus(), spinn2d.SoftPlus()
+    np.savez(os.path.join(HERE, "constants.npz"),
+             k1=a1.k.numpy(), fac1=a1.fac.numpy(), k2=a2.k.numpy(), fac2=a2.fac.numpy())
+
+
+def main():
+    load_reference()
+    torch.set_num_threads(8)
+    constants()
+    mesh_data()
+    op_case_2d("g2d_k1", "gaussian", 4, 3, 61, 1, 11)
+    op_case_2d("s2d_k1", "softplus", 4, 3, 61, 1, 12)
+    op_case_2d("g2d_k3", "gaussian", 3, 4, 50, 3, 13)
+    op_case_2d("s2d_k3", "softplus", 3, 4, 50, 3, 14)
+    op_case_2d("g2d_nofixed", "gaussian", 5, 0, 33, 1, 15)
+    op_case_2d("g2d_one_point", "gaussian", 3, 2, 1, 1, 16)
+    op_case_2d("g2d_fixed_h", "gaussian", 4, 3, 40, 1, 17, fixed_h=True)
+    op_case_2d("s2d_wide", "softplus", 6, 5, 130, 1, 18, lo=-1.5, hi=2.0)
+    op_case_2d("g2d_wide", "gaussian", 6, 5, 130, 2, 19, lo=-1.5, hi=2.0)
+    op_case_1d("g1d_k1", "gaussian", 7, 45, 1, 21)
+    op_case_1d("s1d_k1", "softplus", 7, 45, 1, 22)
+    op_case_1d("g1d_k2", "gaussian", 5, 30, 2, 23)
+    op_case_1d("s1d_nofixed", "softplus", 6, 1, 1, 24, fixed=False)
+
+    from_mod = lambda cls_name, app_name, nn_name, pl_name: (
+        lambda m: getattr(m, app_name)(pde_cls=getattr(m, cls_name), nn_cls=getattr(m, nn_name),
+                                       plotter_cls=getattr(m, pl_name)))
+    trajectory("ode3", "ode3", from_mod("ODESimple", "App1D", "SPINN1D", "Plotter1D"),
+               ["--nodes", "3", "--samples", "60", "--n-train", "300", "--lr", "1e-3", "--tol", "1e-3"])
+    trajectory("ode3_softplus", "ode3", from_mod("ODESimple", "App1D", "SPINN1D", "Plotter1D"),
+               ["--nodes", "3", "--samples", "60", "--n-train", "200", "--lr", "1e-3", "--tol", "1e-3",
+                "--activation", "softplus"])
+    trajectory("poisson2d_sine", "poisson2d_sine", from_mod("Poisson2D", "App2D", "SPINN2D", "Plotter2D"),
+               ["--nodes", "100", "--samples", "400", "--n-train", "300", "--lr", "1e-3", "--tol", "1e-3"])
+    trajectory("poisson2d_sine_softplus", "poisson2d_sine",
+               from_mod("Poisson2D", "App2D", "SPINN2D", "Plotter2D"),
+               ["--nodes", "100", "--samples", "400", "--n-train", "150", "--lr", "1e-3", "--tol", "1e-3",
+                "--activation", "softplus"])
+    trajectory("irreg", "poisson2d_irreg_dom", from_mod("Poisson2D", "App2D", "SPINN2D", "PointCloud"),
+               ["--n-train", "60", "--lr", "1e-3"])
+    trajectory("cavity", "cavity", from_mod("CavityPDE", "App2D", "SPINN2D", "CavityPlotter"),
+               ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4",
+                "--n-train", "100"])
+
+
+if __name__ == "__main__":
+    main()
