@@ -1,0 +1,124 @@
+/* spinn_b200.h -- C ABI of the B200-native SPINN hot path (libspinn_b200.so).
+ *
+ * The reference (nn4pde/SPINN) is pure Python/PyTorch and has no FFI: its
+ * "operator" for this path is the duck-typed nn_cls protocol
+ *   SPINN2D.forward(x, y)   /root/reference/code/spinn2d.py:169-179
+ *   SPINN1D.forward(x)      /root/reference/code/spinn1d.py:147-156
+ * differentiated by the problem classes with torch.autograd.grad
+ *   RegularPDE._compute_derivatives  /root/reference/code/pde2d_base.py:46-62
+ *   BasicODE._compute_derivatives    /root/reference/code/ode_base.py:32-42
+ * and back-propagated by Optimizer.closure  /root/reference/code/common.py:242-248.
+ * The entry points below are what a binding for that path calls instead: one
+ * fused "jets" forward (u and its analytic spatial derivatives at N points
+ * against M nodes) and one fused backward (parameter gradients of
+ * L = sum g*J).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32, owned by the caller
+ *    (PyTorch tensors in practice); nothing is allocated or freed inside;
+ *  - calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*) and
+ *    never synchronise; they are re-entrant (autograd calls the backward from
+ *    its own device thread);
+ *  - return value 0 on success, <0 on error (SPINN_E_*); spinn_last_error()
+ *    returns a thread-local message for the last failure;
+ *  - kind: 0 gaussian (spinn2d.py:191-192, spinn1d.py:176-177),
+ *          1 softplus-hat (spinn2d.py:195-205, spinn1d.py:180-189);
+ *  - level selects which jets are produced / which upstream gradients exist:
+ *      2-D: 0:{u} 1:{u,ux,uy} 2:{u,ux,uy,uxx,uyy} 3:{u,ux,uy,uxx,uyy,uxy}
+ *      1-D: 0:{u} 1:{u,ux}    2:{u,ux,uxx}
+ *  - jets / gjets layout: [n_jets][N][K] (for K=1 every jet is a plain N-vector);
+ *  - centres come as two arrays, free (learnable, spinn2d.py:109-110) and fixed
+ *    (spinn2d.py:112-113); node j<M_free is free, the rest fixed, M=M_free+M_fixed;
+ *  - h: [M], or [1] with h_is_scalar=1 (--fixed-h, spinn2d.py:115-117);
+ *  - W: [K][M] row-major (nn.Linear weight, spinn2d.py:164); bias: [K] or NULL;
+ *  - 1 <= K <= SPINN_MAX_K.
+ */
+#ifndef SPINN_B200_H
+#define SPINN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPINN_ABI_VERSION 1
+#define SPINN_MAX_K 4
+
+#define SPINN_KIND_GAUSSIAN 0
+#define SPINN_KIND_SOFTPLUS 1
+
+#define SPINN_OK 0
+#define SPINN_E_BADARG (-1)
+#define SPINN_E_WORKSPACE (-2)
+#define SPINN_E_CUDA (-3)
+#define SPINN_E_UNSUPPORTED (-4)
+
+int spinn_abi_version(void);
+const char* spinn_last_error(void);
+
+/* number of jets for (dim, level), or <0 if the pair is invalid */
+int spinn_num_jets(int dim, int level);
+
+/* ---- 2-D: replaces SPINN2D.forward + 3x ag.grad (spinn2d.py:169-179, pde2d_base.py:46-62) */
+size_t spinn2d_fwd_workspace_bytes(int N, int M, int K);
+int spinn2d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+                     const float* x, const float* y,
+                     const float* xc_free, const float* yc_free,
+                     const float* xc_fixed, const float* yc_fixed,
+                     const float* h, int h_is_scalar,
+                     const float* W, const float* bias,
+                     float* jets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 2-D backward: replaces loss.backward() through that graph (common.py:242-248).
+ * d_xc/d_yc: [M_free]; d_h: [M] or [1]; d_W: [K][M]; d_bias: [K] or NULL.  Outputs are
+ * overwritten (not accumulated). */
+size_t spinn2d_bwd_workspace_bytes(int N, int M, int K);
+int spinn2d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+                     const float* x, const float* y,
+                     const float* xc_free, const float* yc_free,
+                     const float* xc_fixed, const float* yc_fixed,
+                     const float* h, int h_is_scalar,
+                     const float* W, const float* gjets,
+                     float* d_xc, float* d_yc, float* d_h, float* d_W, float* d_bias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 1-D twins: SPINN1D.forward + 2x ag.grad (spinn1d.py:147-156, ode_base.py:32-42) */
+size_t spinn1d_fwd_workspace_bytes(int N, int M, int K);
+int spinn1d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+                     const float* x, const float* xc_free, const float* xc_fixed,
+                     const float* h, int h_is_scalar,
+                     const float* W, const float* bias,
+                     float* jets, void* workspace, size_t workspace_bytes, void* stream);
+size_t spinn1d_bwd_workspace_bytes(int N, int M, int K);
+int spinn1d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+                     const float* x, const float* xc_free, const float* xc_fixed,
+                     const float* h, int h_is_scalar,
+                     const float* W, const float* gjets,
+                     float* d_xc, float* d_h, float* d_W, float* d_bias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused residual epilogue for the stock Poisson residual
+ * res = scale*(u_xx + u_yy + f(x,y)),  f = amp*sin(kx*x)*sin(ky*y) + f0
+ * (poisson2d_sine.py:16-18: scale .1, amp 20pi^2, kx 2pi, ky 4pi;
+ *  poisson2d_irreg_dom.py:146-147: scale 1, amp 0, f0 1) and loss = sum(res^2)/n_total
+ * (pde2d_base.py:139-141).  Reads jets [5][N], writes gjets [5][N] = dLoss/dJ and adds
+ * the loss into *loss (one float, caller zeroes it).  K=1 only. */
+int spinn2d_poisson_residual(int N, double n_total, const float* x, const float* y,
+                             const float* jets, float scale, float amp, float kx, float ky,
+                             float f0, float* gjets, float* loss, void* workspace,
+                             size_t workspace_bytes, void* stream);
+size_t spinn2d_poisson_residual_workspace_bytes(int N);
+
+/* ---- instruction-throughput microbenchmarks used to measure the roofline
+ * denominators on the box (FP32 FMA, packed FFMA2, MUFU.EX2).  Runs `iters`
+ * dependent-chain iterations per thread on a full grid and returns the number of
+ * lane-operations executed (as double) in *ops; timing is the caller's (CUDA
+ * events on `stream`).  which: 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 FFMA2+EX2 mix (7:1). */
+int spinn_microbench(int which, int iters, int blocks, int threads, float* sink,
+                     double* ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPINN_B200_H */

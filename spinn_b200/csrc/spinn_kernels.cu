@@ -1,0 +1,951 @@
+// spinn_kernels.cu -- sm_100a kernels + C ABI of the SPINN hot path.
+//
+// What the kernels replace in the reference (paths relative to /root/reference):
+//   forward   : SPINN2D.forward / SPINN1D.forward (code/spinn2d.py:169-179,
+//               code/spinn1d.py:147-156) and the three nested autograd.grad
+//               calls of _compute_derivatives (code/pde2d_base.py:46-62,
+//               code/ode_base.py:32-42) -> ONE fused kernel producing all jets;
+//   backward  : loss.backward() through that graph (code/common.py:242-248)
+//               -> ONE fused kernel producing per-node parameter gradients as
+//               per-block partial sums + a small deterministic second stage
+//               (no atomics anywhere).
+// The (N x M) intermediates the reference materialises never exist here: points
+// stream from HBM, nodes live in shared memory (forward) or registers (backward).
+//
+// Two code paths:
+//   * FAST   2-D Gaussian, K=1, level 2: packed f32x2 arithmetic (FFMA2), the
+//            BASELINE headline configuration (4M points x 4096 nodes);
+//   * GENERIC every other (dim, kernel, K<=4, level): scalar arithmetic built on
+//            phi_derivs_* (same tiling, same reduction).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/spinn_b200.h"
+#include "spinn_math.cuh"
+
+using namespace spinn;
+
+// -----------------------------------------------------------------------------
+// host-side utilities
+// -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return fail(SPINN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                          \
+  do {                                                                              \
+    cudaError_t _e = cudaPeekAtLastError();                                         \
+    if (_e != cudaSuccess)                                                          \
+      return fail(SPINN_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// -----------------------------------------------------------------------------
+// node packing
+// SoA rows (each Mp long): 2-D: c, d, h, r, W_0..W_{K-1};  1-D: c, h, r, W_0..
+// padding nodes: c=d=0, h=r=1, W=0 (contribute exactly zero).
+// -----------------------------------------------------------------------------
+template <int DIM>
+__global__ void pack_nodes_soa_kernel(int M, int Mfree, int Mp, int K,
+                                      const float* __restrict__ xf, const float* __restrict__ yf,
+                                      const float* __restrict__ xfix, const float* __restrict__ yfix,
+                                      const float* __restrict__ h, int hs,
+                                      const float* __restrict__ W, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Mp) return;
+  float c = 0.f, d = 0.f, hh = 1.f;
+  if (j < M) {
+    c = j < Mfree ? xf[j] : xfix[j - Mfree];
+    if (DIM == 2) d = j < Mfree ? yf[j] : yfix[j - Mfree];
+    hh = hs ? h[0] : h[j];
+  }
+  int row = 0;
+  out[(size_t)(row++) * Mp + j] = c;
+  if (DIM == 2) out[(size_t)(row++) * Mp + j] = d;
+  out[(size_t)(row++) * Mp + j] = hh;
+  out[(size_t)(row++) * Mp + j] = 1.0f / hh;
+  for (int k = 0; k < K; ++k) out[(size_t)(row++) * Mp + j] = j < M ? W[(size_t)k * M + j] : 0.f;
+}
+
+// fast forward records: one per NODE PAIR (j, j+1), three float4:
+//   {nc_j, nc_j1, nd_j, nd_j1} {rp_j, rp_j1, w0_j, w0_j1} {w1_j, w1_j1, w2_j, w2_j1}
+__global__ void pack_nodes_g2fwd_kernel(int M, int Mfree, int npairs,
+                                        const float* __restrict__ xf, const float* __restrict__ yf,
+                                        const float* __restrict__ xfix, const float* __restrict__ yfix,
+                                        const float* __restrict__ h, int hs,
+                                        const float* __restrict__ W, float4* __restrict__ recs) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  G2FwdNode n[2];
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    int j = 2 * p + l;
+    if (j < M) {
+      float c = j < Mfree ? xf[j] : xfix[j - Mfree];
+      float d = j < Mfree ? yf[j] : yfix[j - Mfree];
+      n[l] = g2_fwd_node(c, d, hs ? h[0] : h[j], W[j]);
+    } else {
+      n[l] = g2_fwd_node(0.f, 0.f, 1.f, 0.f);
+    }
+  }
+  recs[3 * (size_t)p + 0] = make_float4(n[0].nc, n[1].nc, n[0].nd, n[1].nd);
+  recs[3 * (size_t)p + 1] = make_float4(n[0].rp, n[1].rp, n[0].w0, n[1].w0);
+  recs[3 * (size_t)p + 2] = make_float4(n[0].w1, n[1].w1, n[0].w2, n[1].w2);
+}
+
+// fast backward records: one per POINT PAIR (i, i+1), four float4:
+//   {x_i,x_i1,y_i,y_i1} {g0,g0',g1,g1'} {g2,g2',g3,g3'} {g4,g4',0,0}
+__global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict__ x,
+                                         const float* __restrict__ y, const float* __restrict__ g,
+                                         float4* __restrict__ recs) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N2) return;
+  int i0 = 2 * p, i1 = 2 * p + 1;
+  bool v1 = i1 < N;
+  size_t n = (size_t)N;
+  float x0 = x[i0], y0 = y[i0];
+  float x1 = v1 ? x[i1] : x0, y1 = v1 ? y[i1] : y0;
+  float a[5], b[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    a[k] = g[k * n + i0];
+    b[k] = v1 ? g[k * n + i1] : 0.f;
+  }
+  recs[4 * (size_t)p + 0] = make_float4(x0, x1, y0, y1);
+  recs[4 * (size_t)p + 1] = make_float4(a[0], b[0], a[1], b[1]);
+  recs[4 * (size_t)p + 2] = make_float4(a[2], b[2], a[3], b[3]);
+  recs[4 * (size_t)p + 3] = make_float4(a[4], b[4], 0.f, 0.f);
+}
+
+// -----------------------------------------------------------------------------
+// FAST forward: 2-D Gaussian, K=1.  Thread = P consecutive points (registers),
+// node-pair records broadcast from shared memory, packed f32x2 math where the two
+// lanes are the two nodes of a pair.
+// -----------------------------------------------------------------------------
+constexpr int FWD_THREADS = 256;
+
+template <int P, bool MIXED>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
+                const float4* __restrict__ recs, int npairs, int tile_pairs,
+                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+  constexpr int NJ = MIXED ? 6 : 5;
+  extern __shared__ float4 sm4[];
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * P;
+
+  float px[P], py[P];
+  if (P == 4 && vec_ok && i0 + 3 < N) {
+    float4 a = *reinterpret_cast<const float4*>(x + i0);
+    float4 b = *reinterpret_cast<const float4*>(y + i0);
+    px[0] = a.x; px[1 % P] = a.y; px[2 % P] = a.z; px[3 % P] = a.w;
+    py[0] = b.x; py[1 % P] = b.y; py[2 % P] = b.z; py[3 % P] = b.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      px[q] = (i0 + q < N) ? x[i0 + q] : 0.f;
+      py[q] = (i0 + q < N) ? y[i0 + q] : 0.f;
+    }
+  }
+  float2 x2[P], y2[P], acc[P][NJ];
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    x2[q] = f2dup(px[q]);
+    y2[q] = f2dup(py[q]);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
+  }
+
+  for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
+    const int n = min(tile_pairs, npairs - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) sm4[e] = recs[3 * (size_t)t0 + e];
+    __syncthreads();
+#pragma unroll 2
+    for (int p = 0; p < n; ++p) {
+      const float4 A = sm4[3 * p + 0], B = sm4[3 * p + 1], C = sm4[3 * p + 2];
+      const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
+      const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
+#pragma unroll
+      for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+    }
+  }
+
+  const float b0 = bias ? bias[0] : 0.f;
+  float out[NJ][P];
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) out[a][q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
+  if (P == 4 && vec_ok && i0 + 3 < N) {
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+      *reinterpret_cast<float4*>(jets + (size_t)a * N + i0) =
+          make_float4(out[a][0], out[a][1 % P], out[a][2 % P], out[a][3 % P]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+      if (i0 + q < N)
+#pragma unroll
+        for (int a = 0; a < NJ; ++a) jets[(size_t)a * N + i0 + q] = out[a][q];
+  }
+}
+
+// -----------------------------------------------------------------------------
+// FAST backward: 2-D Gaussian, K=1, level 2.  Thread = Q nodes (registers), point
+// pair records broadcast from shared memory, packed lanes = the two points of a
+// pair.  grid = (node groups, point chunks); every block writes its partial sums
+// to partials[chunk][row][node]; finalize_kernel reduces over chunks in order.
+// Two-level accumulation (per tile, then per chunk) keeps fp32 round-off at the
+// level of the reference's pairwise torch.sum.
+// -----------------------------------------------------------------------------
+constexpr int BWD_THREADS = 128;
+constexpr int BWD_TILE_PAIRS = 256;    // point pairs per smem tile (16 KB)
+
+template <int Q>
+__global__ void __launch_bounds__(BWD_THREADS, 4)
+g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
+                const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
+  __shared__ float4 sm4[4 * BWD_TILE_PAIRS];
+  const int jbase = blockIdx.x * (Q * BWD_THREADS) + threadIdx.x;
+  float2 nc[Q], nd[Q], rp[Q], nrt[Q], rho[Q], nk1[Q], k2p[Q];
+  float hq[Q], wq[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int j = jbase + q * BWD_THREADS;
+    const float c = soa[j], d = soa[(size_t)Mp + j];
+    hq[q] = soa[2 * (size_t)Mp + j];
+    wq[q] = soa[4 * (size_t)Mp + j];
+    const G2BwdNode n = g2_bwd_node(c, d, hq[q]);
+    nc[q] = f2dup(n.nc); nd[q] = f2dup(n.nd); rp[q] = f2dup(n.rp); nrt[q] = f2dup(n.nrt);
+    rho[q] = f2dup(n.rho); nk1[q] = f2dup(n.nk1); k2p[q] = f2dup(n.k2p);
+  }
+  float tot[Q][4];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) tot[q][a] = 0.f;
+
+  const int p_begin = blockIdx.y * pairs_per_chunk;
+  const int p_end = min(N2, p_begin + pairs_per_chunk);
+  for (int t0 = p_begin; t0 < p_end; t0 += BWD_TILE_PAIRS) {
+    const int n = min(BWD_TILE_PAIRS, p_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * n; e += BWD_THREADS) sm4[e] = ptrecs[4 * (size_t)t0 + e];
+    __syncthreads();
+    float2 acc[Q][4];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc[q][a] = f2(0.f, 0.f);
+#pragma unroll 2
+    for (int p = 0; p < n; ++p) {
+      const float4 A = sm4[4 * p + 0], B = sm4[4 * p + 1], C = sm4[4 * p + 2], D = sm4[4 * p + 3];
+      const float2 x2 = f2(A.x, A.y), y2 = f2(A.z, A.w);
+      const float2 g0 = f2(B.x, B.y), g1 = f2(B.z, B.w), g2 = f2(C.x, C.y), g3 = f2(C.z, C.w);
+      const float2 g4 = f2(D.x, D.y);
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q],
+                    acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
+  }
+  // rows: 0 dc, 1 dd, 2 dh, 3 dW
+  float* out = partials + (size_t)blockIdx.y * 4 * Mp;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int j = jbase + q * BWD_THREADS;
+    float dW, dc, dd, dh;
+    g2_bwd_finish(hq[q], wq[q], tot[q][0], tot[q][1], tot[q][2], tot[q][3], &dW, &dc, &dd, &dh);
+    out[j] = dc;
+    out[(size_t)Mp + j] = dd;
+    out[2 * (size_t)Mp + j] = dh;
+    out[3 * (size_t)Mp + j] = dW;
+  }
+}
+
+// -----------------------------------------------------------------------------
+// GENERIC forward: thread = one point, nodes tiled through shared memory (SoA).
+// -----------------------------------------------------------------------------
+constexpr int GEN_THREADS = 128;
+constexpr int GEN_TILE_NODES = 512;
+constexpr int GEN_TILE_POINTS = 256;
+
+template <int DIM, int KIND, int K, int LEVEL>
+__global__ void __launch_bounds__(GEN_THREADS)
+fwd_generic_kernel(int N, int Mp, const float* __restrict__ x, const float* __restrict__ y,
+                   const float* __restrict__ soa, const float* __restrict__ bias,
+                   float* __restrict__ jets) {
+  constexpr int NJ = njets(DIM, LEVEL);
+  constexpr int NROW = DIM + 1 + K;              // c,(d),r,W_k  (the h row is skipped)
+  constexpr int TN = GEN_TILE_NODES;
+  __shared__ float sm[NROW * TN];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float px = i < N ? x[i] : 0.f;
+  const float py = (DIM == 2 && i < N) ? y[i] : 0.f;
+  float acc[NJ][K];
+#pragma unroll
+  for (int a = 0; a < NJ; ++a)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[a][k] = 0.f;
+
+  for (int t0 = 0; t0 < Mp; t0 += TN) {
+    const int n = min(TN, Mp - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < NROW * n; e += blockDim.x) {
+      const int row = e / n, col = e - row * n;
+      const int srow = row < DIM ? row : row + 1;   // skip h
+      sm[row * TN + col] = soa[(size_t)srow * Mp + t0 + col];
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+      float Wk[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) Wk[k] = sm[(DIM + 1 + k) * TN + j];
+      if (DIM == 2)
+        generic_fwd_pair<DIM, KIND, K, LEVEL>(px - sm[j], py - sm[TN + j], sm[2 * TN + j], Wk, acc);
+      else
+        generic_fwd_pair<DIM, KIND, K, LEVEL>(px - sm[j], 0.f, sm[TN + j], Wk, acc);
+    }
+  }
+  if (i < N) {
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        jets[((size_t)a * N + i) * K + k] = acc[a][k] + ((a == 0 && bias) ? bias[k] : 0.f);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// GENERIC backward: thread = one node, points tiled through shared memory.
+// partial rows: 0 dc, (1 dd), DIM dh, DIM+1+k dW_k.
+// -----------------------------------------------------------------------------
+template <int DIM, int KIND, int K, int LEVEL>
+__global__ void __launch_bounds__(GEN_THREADS)
+bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x,
+                   const float* __restrict__ y, const float* __restrict__ gj,
+                   const float* __restrict__ soa, float* __restrict__ partials) {
+  constexpr int NG = njets(DIM, LEVEL);
+  constexpr int TP = GEN_TILE_POINTS;
+  constexpr int NACC = DIM + 1 + K;
+  __shared__ float spx[TP], spy[DIM == 2 ? TP : 1], sg[NG * K * TP];
+  const int j = blockIdx.x * GEN_THREADS + threadIdx.x;     // < Mp (Mp multiple of GEN_THREADS)
+  int row = 0;
+  const float c = soa[(size_t)(row++) * Mp + j];
+  const float dn = DIM == 2 ? soa[(size_t)(row++) * Mp + j] : 0.f;
+  row++;  // h
+  const float r = soa[(size_t)(row++) * Mp + j];
+  float Wk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) Wk[k] = soa[(size_t)(row++) * Mp + j];
+
+  float tot[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) tot[a] = 0.f;
+
+  const long long i_begin = (long long)blockIdx.y * pts_per_chunk;
+  const long long i_end = min((long long)N, i_begin + pts_per_chunk);
+  for (long long t0 = i_begin; t0 < i_end; t0 += TP) {
+    const int n = (int)min((long long)TP, i_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += GEN_THREADS) {
+      spx[e] = x[t0 + e];
+      if (DIM == 2) spy[e] = y[t0 + e];
+#pragma unroll
+      for (int a = 0; a < NG; ++a)
+#pragma unroll
+        for (int k = 0; k < K; ++k) sg[(a * K + k) * TP + e] = gj[((size_t)a * N + t0 + e) * K + k];
+    }
+    __syncthreads();
+    float acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float X = spx[i] - c;
+      const float Y = DIM == 2 ? spy[i] - dn : 0.f;
+      generic_bwd_pair<DIM, KIND, K, LEVEL>(X, Y, r, Wk, sg + i, TP, acc);
+    }
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) tot[a] += acc[a];
+  }
+  float* out = partials + (size_t)blockIdx.y * NACC * Mp;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) out[(size_t)a * Mp + j] = tot[a];
+}
+
+// -----------------------------------------------------------------------------
+// second stage: bias gradient partials, chunk reduction, scalar-h reduction
+// -----------------------------------------------------------------------------
+constexpr int BIAS_BLOCKS = 64;
+
+__global__ void __launch_bounds__(256)
+bias_partial_kernel(int N, int K, const float* __restrict__ g0, float* __restrict__ bpart) {
+  __shared__ float red[SPINN_MAX_K][8];
+  float s[SPINN_MAX_K] = {0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x)
+    for (int k = 0; k < K; ++k) s[k] += g0[(size_t)i * K + k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < K; ++k) {
+    float v = s[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    bpart[blockIdx.x * K + threadIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+finalize_kernel(int dim, int K, int M, int Mfree, int Mp, int C, const float* __restrict__ partials,
+                const float* __restrict__ bpart, int nb, float* __restrict__ d_xc,
+                float* __restrict__ d_yc, float* __restrict__ d_h, float* __restrict__ d_W,
+                float* __restrict__ d_bias) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nacc = dim + 1 + K;
+  if (j < M) {
+    for (int a = 0; a < nacc; ++a) {
+      double s = 0.0;
+      for (int c = 0; c < C; ++c) s += (double)partials[((size_t)c * nacc + a) * Mp + j];
+      const float v = (float)s;
+      if (a == 0) { if (j < Mfree) d_xc[j] = v; }
+      else if (dim == 2 && a == 1) { if (j < Mfree) d_yc[j] = v; }
+      else if (a == dim) d_h[j] = v;
+      else d_W[(size_t)(a - dim - 1) * M + j] = v;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < K && d_bias != nullptr) {
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += (double)bpart[b * K + threadIdx.x];
+    d_bias[threadIdx.x] = (float)s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sum_to_scalar_kernel(int n, const float* __restrict__ v, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)red[0];
+}
+
+// -----------------------------------------------------------------------------
+// Poisson residual epilogue (K=1): res, loss partials, upstream jets gradients
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+poisson_residual_kernel(int N, float inv_n, const float* __restrict__ x, const float* __restrict__ y,
+                        const float* __restrict__ jets, float scale, float amp, float kx, float ky,
+                        float f0, float* __restrict__ gj, float* __restrict__ lpart) {
+  __shared__ float red[8];
+  const size_t n = (size_t)N;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float f = fmaf(amp * sinf(kx * x[i]), sinf(ky * y[i]), f0);
+    const float res = scale * (jets[3 * n + i] + jets[4 * n + i] + f);
+    s = fmaf(res, res, s);
+    const float g = 2.f * scale * res * inv_n;
+    gj[i] = 0.f; gj[n + i] = 0.f; gj[2 * n + i] = 0.f;
+    gj[3 * n + i] = g; gj[4 * n + i] = g;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    lpart[blockIdx.x] = v * inv_n;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += (float)red[0];
+}
+
+// -----------------------------------------------------------------------------
+// microbenchmarks (roofline denominators measured on the box)
+// -----------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256)
+microbench_kernel(int iters, float* sink) {
+  const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
+  float2 a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = f2(seed + k, seed - k);
+  const float2 m = f2(0.999999f, 1.000001f), c = f2(1e-9f, -1e-9f);
+  for (int it = 0; it < iters; ++it) {
+    if (WHICH == 0) {          // scalar FFMA, 16 independent chains
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k].x = fmaf(a[k].x, m.x, c.x); a[k].y = fmaf(a[k].y, m.y, c.y); }
+    } else if (WHICH == 1) {   // packed FFMA2, 8 independent chains
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = f2fma(a[k], m, c);
+    } else if (WHICH == 2) {   // MUFU.EX2, 16 independent chains
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k].x = ex2f_fast(a[k].x); a[k].y = ex2f_fast(a[k].y); }
+    } else {                   // the forward kernel's mix: 14 packed ops + 2 ex2 per group
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        float2 t = a[k];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) { t = f2fma(t, m, c); a[k + 1] = f2fma(a[k + 1], m, t); }
+        a[k] = f2(ex2f_fast(-fabsf(t.x)), ex2f_fast(-fabsf(t.y)));
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y;
+  if (s == 123.456f) sink[0] = s;
+}
+
+// -----------------------------------------------------------------------------
+// planning
+// -----------------------------------------------------------------------------
+struct FwdPlan {
+  bool fast;
+  int Mp;          // generic: padded node count (multiple of GEN_THREADS)
+  int npairs;      // fast: node pairs
+  size_t ws_bytes;
+};
+
+static bool fwd_is_fast(int dim, int kind, int level, int K) {
+  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && (level == 2 || level == 3);
+}
+
+static FwdPlan plan_fwd(int dim, int kind, int level, int M, int K) {
+  FwdPlan p;
+  p.fast = fwd_is_fast(dim, kind, level, K);
+  p.Mp = round_up_i(M, GEN_THREADS);
+  p.npairs = (M + 1) / 2;
+  const size_t gen = (size_t)(dim + 2 + K) * p.Mp * sizeof(float);
+  const size_t fast = (size_t)3 * p.npairs * sizeof(float4);
+  p.ws_bytes = align_up(gen > fast ? gen : fast, 256);
+  return p;
+}
+
+static size_t fwd_ws_bytes_any(int dim, int M, int K) {
+  // upper bound over kind/level so that the caller can size once per (M, K)
+  FwdPlan a = plan_fwd(dim, SPINN_KIND_GAUSSIAN, 2, M, K);
+  return a.ws_bytes;
+}
+
+struct BwdPlan {
+  bool fast;
+  int Mp;              // padded node count
+  int node_groups;
+  int chunks;          // point chunks (grid.y)
+  int per_chunk;       // points (generic) or point pairs (fast) per chunk
+  int N2;              // fast: point pairs
+  size_t off_soa, off_pts, off_part, off_bias, off_htmp, ws_bytes;
+};
+
+constexpr int BWD_Q = 2;
+
+static bool bwd_is_fast(int dim, int kind, int level, int K) {
+  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && level == 2;
+}
+
+static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool worst) {
+  BwdPlan p;
+  p.fast = bwd_is_fast(dim, kind, level, K);
+  const int sms = sm_count();
+  const int nacc = dim + 1 + K;
+  // worst-case sizing uses the larger padding and the larger chunk count of the two paths
+  const int group_fast = BWD_Q * BWD_THREADS, group_gen = GEN_THREADS;
+  const int Mp_fast = round_up_i(M, group_fast), Mp_gen = round_up_i(M, group_gen);
+  p.N2 = (N + 1) / 2;
+  auto chunks_for = [&](int groups, long long units, int tile, int blocks_per_sm, int* per_chunk) {
+    long long target = (long long)sms * blocks_per_sm * 2;      // ~2 waves of resident blocks
+    int c = (int)((target + groups - 1) / groups);
+    if (c < 1) c = 1;
+    long long per = (units + c - 1) / c;
+    per = (per + tile - 1) / tile * tile;
+    if (per < tile) per = tile;
+    *per_chunk = (int)per;
+    c = (int)((units + per - 1) / per);
+    return c < 1 ? 1 : c;
+  };
+  int pc_fast = 0, pc_gen = 0;
+  const int c_fast = chunks_for(Mp_fast / group_fast, p.N2, BWD_TILE_PAIRS, 4, &pc_fast);
+  const int c_gen = chunks_for(Mp_gen / group_gen, N, GEN_TILE_POINTS, 4, &pc_gen);
+  if (p.fast) { p.Mp = Mp_fast; p.node_groups = Mp_fast / group_fast; p.chunks = c_fast; p.per_chunk = pc_fast; }
+  else { p.Mp = Mp_gen; p.node_groups = Mp_gen / group_gen; p.chunks = c_gen; p.per_chunk = pc_gen; }
+  const int Mp_w = worst ? (Mp_fast > Mp_gen ? Mp_fast : Mp_gen) : p.Mp;
+  const int c_w = worst ? (c_fast > c_gen ? c_fast : c_gen) : p.chunks;
+  size_t off = 0;
+  p.off_soa = off;  off += align_up((size_t)(dim + 2 + K) * Mp_w * sizeof(float), 256);
+  p.off_pts = off;  off += (worst || p.fast) ? align_up((size_t)4 * p.N2 * sizeof(float4), 256) : 0;
+  p.off_part = off; off += align_up((size_t)c_w * nacc * Mp_w * sizeof(float), 256);
+  p.off_bias = off; off += align_up((size_t)BIAS_BLOCKS * SPINN_MAX_K * sizeof(float), 256);
+  p.off_htmp = off; off += align_up((size_t)Mp_w * sizeof(float), 256);
+  p.ws_bytes = off;
+  return p;
+}
+
+// -----------------------------------------------------------------------------
+// dispatch helpers
+// -----------------------------------------------------------------------------
+template <int DIM, int KIND, int K>
+static void launch_fwd_generic_level(int level, int N, int Mp, const float* x, const float* y,
+                                     const float* soa, const float* bias, float* jets,
+                                     cudaStream_t s) {
+  dim3 grid(ceil_div_i(N, GEN_THREADS)), block(GEN_THREADS);
+  switch (level) {
+    case 0: fwd_generic_kernel<DIM, KIND, K, 0><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets); break;
+    case 1: fwd_generic_kernel<DIM, KIND, K, 1><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets); break;
+    case 2: fwd_generic_kernel<DIM, KIND, K, 2><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets); break;
+    default:
+      if (DIM == 2)
+        fwd_generic_kernel<DIM, KIND, K, (DIM == 2 ? 3 : 2)><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets);
+      break;
+  }
+}
+
+template <int DIM, int KIND>
+static void launch_fwd_generic_k(int K, int level, int N, int Mp, const float* x, const float* y,
+                                 const float* soa, const float* bias, float* jets, cudaStream_t s) {
+  switch (K) {
+    case 1: launch_fwd_generic_level<DIM, KIND, 1>(level, N, Mp, x, y, soa, bias, jets, s); break;
+    case 2: launch_fwd_generic_level<DIM, KIND, 2>(level, N, Mp, x, y, soa, bias, jets, s); break;
+    case 3: launch_fwd_generic_level<DIM, KIND, 3>(level, N, Mp, x, y, soa, bias, jets, s); break;
+    default: launch_fwd_generic_level<DIM, KIND, 4>(level, N, Mp, x, y, soa, bias, jets, s); break;
+  }
+}
+
+template <int DIM, int KIND, int K>
+static void launch_bwd_generic_level(int level, dim3 grid, int N, int Mp, int per_chunk,
+                                     const float* x, const float* y, const float* gj,
+                                     const float* soa, float* partials, cudaStream_t s) {
+  dim3 block(GEN_THREADS);
+  switch (level) {
+    case 0: bwd_generic_kernel<DIM, KIND, K, 0><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
+    case 1: bwd_generic_kernel<DIM, KIND, K, 1><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
+    case 2: bwd_generic_kernel<DIM, KIND, K, 2><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
+    default:
+      if (DIM == 2)
+        bwd_generic_kernel<DIM, KIND, K, (DIM == 2 ? 3 : 2)><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials);
+      break;
+  }
+}
+
+template <int DIM, int KIND>
+static void launch_bwd_generic_k(int K, int level, dim3 grid, int N, int Mp, int per_chunk,
+                                 const float* x, const float* y, const float* gj, const float* soa,
+                                 float* partials, cudaStream_t s) {
+  switch (K) {
+    case 1: launch_bwd_generic_level<DIM, KIND, 1>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
+    case 2: launch_bwd_generic_level<DIM, KIND, 2>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
+    case 3: launch_bwd_generic_level<DIM, KIND, 3>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
+    default: launch_bwd_generic_level<DIM, KIND, 4>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
+  }
+}
+
+static int check_common(int dim, int kind, int level, int N, int M_free, int M_fixed, int K) {
+  if (kind != SPINN_KIND_GAUSSIAN && kind != SPINN_KIND_SOFTPLUS)
+    return fail(SPINN_E_BADARG, "kind must be 0 (gaussian) or 1 (softplus-hat), got %d", kind);
+  if (spinn_num_jets(dim, level) < 0)
+    return fail(SPINN_E_BADARG, "invalid level %d for dim %d", level, dim);
+  if (N < 0 || M_free < 0 || M_fixed < 0 || M_free + M_fixed <= 0)
+    return fail(SPINN_E_BADARG, "bad sizes N=%d M_free=%d M_fixed=%d", N, M_free, M_fixed);
+  if (K < 1) return fail(SPINN_E_BADARG, "K must be >= 1, got %d", K);
+  if (K > SPINN_MAX_K)
+    return fail(SPINN_E_UNSUPPORTED, "K=%d outputs not supported (max %d)", K, SPINN_MAX_K);
+  return SPINN_OK;
+}
+
+// -----------------------------------------------------------------------------
+// forward implementation shared by the 1-D / 2-D entry points
+// -----------------------------------------------------------------------------
+static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_fixed, int K,
+                         const float* x, const float* y, const float* xf, const float* yf,
+                         const float* xfix, const float* yfix, const float* h, int hs,
+                         const float* W, const float* bias, float* jets, void* ws, size_t ws_bytes,
+                         void* stream) {
+  int rc = check_common(dim, kind, level, N, M_free, M_fixed, K);
+  if (rc) return rc;
+  if (N == 0) return SPINN_OK;
+  const int M = M_free + M_fixed;
+  if (!x || (dim == 2 && !y) || !h || !W || !jets || (M_free && !xf) || (M_fixed && !xfix) ||
+      (dim == 2 && ((M_free && !yf) || (M_fixed && !yfix))))
+    return fail(SPINN_E_BADARG, "null pointer argument in jets_fwd");
+  cudaStream_t s = (cudaStream_t)stream;
+  const FwdPlan p = plan_fwd(dim, kind, level, M, K);
+  if (!ws || ws_bytes < p.ws_bytes)
+    return fail(SPINN_E_WORKSPACE, "forward workspace too small: %zu < %zu", ws_bytes, p.ws_bytes);
+
+  if (p.fast) {
+    float4* recs = (float4*)ws;
+    pack_nodes_g2fwd_kernel<<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
+                                                                      xfix, yfix, h, hs, W, recs);
+    LAUNCH_CHECK("pack_nodes_g2fwd_kernel");
+    const int tile_pairs = p.npairs < 2048 ? p.npairs : 2048;
+    const size_t smem = (size_t)3 * tile_pairs * sizeof(float4);
+    const int vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)jets) % 16 == 0) && (N % 4 == 0);
+    const bool mixed = level == 3;
+    const bool big = (long long)N >= (long long)4 * FWD_THREADS * sm_count();
+#define SPINN_LAUNCH_FAST_FWD(P_, MIX_)                                                        \
+  do {                                                                                         \
+    auto kfn = g2k1_fwd_kernel<P_, MIX_>;                                                      \
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));  \
+    const int threads = (P_ == 1 && N < 4096) ? 64 : FWD_THREADS;                              \
+    const int blocks = ceil_div_i(N, (long long)threads * P_);                                 \
+    kfn<<<blocks, threads, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok); \
+  } while (0)
+    if (big) { if (mixed) SPINN_LAUNCH_FAST_FWD(4, true); else SPINN_LAUNCH_FAST_FWD(4, false); }
+    else     { if (mixed) SPINN_LAUNCH_FAST_FWD(1, true); else SPINN_LAUNCH_FAST_FWD(1, false); }
+#undef SPINN_LAUNCH_FAST_FWD
+    LAUNCH_CHECK("g2k1_fwd_kernel");
+    return SPINN_OK;
+  }
+
+  float* soa = (float*)ws;
+  if (dim == 2)
+    pack_nodes_soa_kernel<2><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, yf, xfix, yfix, h, hs, W, soa);
+  else
+    pack_nodes_soa_kernel<1><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, nullptr, xfix, nullptr, h, hs, W, soa);
+  LAUNCH_CHECK("pack_nodes_soa_kernel");
+  if (dim == 2) {
+    if (kind == SPINN_KIND_GAUSSIAN) launch_fwd_generic_k<2, GAUSSIAN>(K, level, N, p.Mp, x, y, soa, bias, jets, s);
+    else launch_fwd_generic_k<2, SOFTPLUS>(K, level, N, p.Mp, x, y, soa, bias, jets, s);
+  } else {
+    if (kind == SPINN_KIND_GAUSSIAN) launch_fwd_generic_k<1, GAUSSIAN>(K, level, N, p.Mp, x, nullptr, soa, bias, jets, s);
+    else launch_fwd_generic_k<1, SOFTPLUS>(K, level, N, p.Mp, x, nullptr, soa, bias, jets, s);
+  }
+  LAUNCH_CHECK("fwd_generic_kernel");
+  return SPINN_OK;
+}
+
+static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_fixed, int K,
+                         const float* x, const float* y, const float* xf, const float* yf,
+                         const float* xfix, const float* yfix, const float* h, int hs,
+                         const float* W, const float* gj, float* d_xc, float* d_yc, float* d_h,
+                         float* d_W, float* d_bias, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_common(dim, kind, level, N, M_free, M_fixed, K);
+  if (rc) return rc;
+  const int M = M_free + M_fixed;
+  if (!h || !W || !d_h || !d_W || (M_free && (!xf || !d_xc)) || (M_fixed && !xfix) ||
+      (dim == 2 && ((M_free && (!yf || !d_yc)) || (M_fixed && !yfix))))
+    return fail(SPINN_E_BADARG, "null pointer argument in jets_bwd");
+  if (N > 0 && (!x || (dim == 2 && !y) || !gj))
+    return fail(SPINN_E_BADARG, "null point/gradient pointer in jets_bwd");
+  cudaStream_t s = (cudaStream_t)stream;
+  const BwdPlan p = plan_bwd(dim, kind, level, N, M, K, false);
+  if (!ws || ws_bytes < p.ws_bytes)
+    return fail(SPINN_E_WORKSPACE, "backward workspace too small: %zu < %zu", ws_bytes, p.ws_bytes);
+  char* base = (char*)ws;
+  float* soa = (float*)(base + p.off_soa);
+  float* partials = (float*)(base + p.off_part);
+  float* bpart = (float*)(base + p.off_bias);
+  float* htmp = (float*)(base + p.off_htmp);
+  const int nacc = dim + 1 + K;
+
+  if (N == 0) {  // empty point set: all gradients are zero
+    if (M_free) CUDA_TRY(cudaMemsetAsync(d_xc, 0, sizeof(float) * M_free, s));
+    if (dim == 2 && M_free) CUDA_TRY(cudaMemsetAsync(d_yc, 0, sizeof(float) * M_free, s));
+    CUDA_TRY(cudaMemsetAsync(d_h, 0, sizeof(float) * (hs ? 1 : M), s));
+    CUDA_TRY(cudaMemsetAsync(d_W, 0, sizeof(float) * (size_t)K * M, s));
+    if (d_bias) CUDA_TRY(cudaMemsetAsync(d_bias, 0, sizeof(float) * K, s));
+    return SPINN_OK;
+  }
+
+  if (dim == 2)
+    pack_nodes_soa_kernel<2><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, yf, xfix, yfix, h, hs, W, soa);
+  else
+    pack_nodes_soa_kernel<1><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, nullptr, xfix, nullptr, h, hs, W, soa);
+  LAUNCH_CHECK("pack_nodes_soa_kernel");
+
+  dim3 grid(p.node_groups, p.chunks);
+  if (p.fast) {
+    float4* ptrecs = (float4*)(base + p.off_pts);
+    pack_points_g2bwd_kernel<<<ceil_div_i(p.N2, 256), 256, 0, s>>>(N, p.N2, x, y, gj, ptrecs);
+    LAUNCH_CHECK("pack_points_g2bwd_kernel");
+    g2k1_bwd_kernel<BWD_Q><<<grid, BWD_THREADS, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);
+    LAUNCH_CHECK("g2k1_bwd_kernel");
+  } else {
+    if (dim == 2) {
+      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<2, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, soa, partials, s);
+      else launch_bwd_generic_k<2, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, soa, partials, s);
+    } else {
+      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<1, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, soa, partials, s);
+      else launch_bwd_generic_k<1, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, soa, partials, s);
+    }
+    LAUNCH_CHECK("bwd_generic_kernel");
+  }
+  int nb = 0;
+  if (d_bias) {
+    nb = ceil_div_i(N, 256) < BIAS_BLOCKS ? ceil_div_i(N, 256) : BIAS_BLOCKS;
+    bias_partial_kernel<<<nb, 256, 0, s>>>(N, K, gj, bpart);
+    LAUNCH_CHECK("bias_partial_kernel");
+  }
+  finalize_kernel<<<ceil_div_i(M, 128), 128, 0, s>>>(dim, K, M, M_free, p.Mp, p.chunks, partials, bpart,
+                                                     nb, d_xc, d_yc, hs ? htmp : d_h, d_W, d_bias);
+  LAUNCH_CHECK("finalize_kernel");
+  if (hs) {
+    sum_to_scalar_kernel<<<1, 256, 0, s>>>(M, htmp, d_h);
+    LAUNCH_CHECK("sum_to_scalar_kernel");
+  }
+  (void)nacc;
+  return SPINN_OK;
+}
+
+// -----------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------
+extern "C" {
+
+int spinn_abi_version(void) { return SPINN_ABI_VERSION; }
+const char* spinn_last_error(void) { return g_err; }
+
+int spinn_num_jets(int dim, int level) {
+  if (dim == 2 && level >= 0 && level <= 3) return njets(2, level);
+  if (dim == 1 && level >= 0 && level <= 2) return njets(1, level);
+  return -1;
+}
+
+size_t spinn2d_fwd_workspace_bytes(int N, int M, int K) { (void)N; return fwd_ws_bytes_any(2, M, K); }
+size_t spinn1d_fwd_workspace_bytes(int N, int M, int K) { (void)N; return fwd_ws_bytes_any(1, M, K); }
+size_t spinn2d_bwd_workspace_bytes(int N, int M, int K) {
+  return plan_bwd(2, SPINN_KIND_GAUSSIAN, 2, N, M, K, true).ws_bytes;
+}
+size_t spinn1d_bwd_workspace_bytes(int N, int M, int K) {
+  return plan_bwd(1, SPINN_KIND_GAUSSIAN, 2, N, M, K, true).ws_bytes;
+}
+
+int spinn2d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+                     const float* y, const float* xc_free, const float* yc_free,
+                     const float* xc_fixed, const float* yc_fixed, const float* h, int h_is_scalar,
+                     const float* W, const float* bias, float* jets, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return jets_fwd_impl(2, kind, level, N, M_free, M_fixed, K, x, y, xc_free, yc_free, xc_fixed,
+                       yc_fixed, h, h_is_scalar, W, bias, jets, workspace, workspace_bytes, stream);
+}
+
+int spinn1d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+                     const float* xc_free, const float* xc_fixed, const float* h, int h_is_scalar,
+                     const float* W, const float* bias, float* jets, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return jets_fwd_impl(1, kind, level, N, M_free, M_fixed, K, x, nullptr, xc_free, nullptr, xc_fixed,
+                       nullptr, h, h_is_scalar, W, bias, jets, workspace, workspace_bytes, stream);
+}
+
+int spinn2d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+                     const float* y, const float* xc_free, const float* yc_free,
+                     const float* xc_fixed, const float* yc_fixed, const float* h, int h_is_scalar,
+                     const float* W, const float* gjets, float* d_xc, float* d_yc, float* d_h,
+                     float* d_W, float* d_bias, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return jets_bwd_impl(2, kind, level, N, M_free, M_fixed, K, x, y, xc_free, yc_free, xc_fixed,
+                       yc_fixed, h, h_is_scalar, W, gjets, d_xc, d_yc, d_h, d_W, d_bias, workspace,
+                       workspace_bytes, stream);
+}
+
+int spinn1d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+                     const float* xc_free, const float* xc_fixed, const float* h, int h_is_scalar,
+                     const float* W, const float* gjets, float* d_xc, float* d_h, float* d_W,
+                     float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
+  return jets_bwd_impl(1, kind, level, N, M_free, M_fixed, K, x, nullptr, xc_free, nullptr, xc_fixed,
+                       nullptr, h, h_is_scalar, W, gjets, d_xc, nullptr, d_h, d_W, d_bias, workspace,
+                       workspace_bytes, stream);
+}
+
+size_t spinn2d_poisson_residual_workspace_bytes(int N) {
+  (void)N;
+  return align_up((size_t)1024 * sizeof(float), 256);
+}
+
+int spinn2d_poisson_residual(int N, double n_total, const float* x, const float* y,
+                             const float* jets, float scale, float amp, float kx, float ky, float f0,
+                             float* gjets, float* loss, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (N < 0 || n_total <= 0.0) return fail(SPINN_E_BADARG, "bad N/n_total");
+  if (N == 0) return SPINN_OK;
+  if (!x || !y || !jets || !gjets || !loss) return fail(SPINN_E_BADARG, "null pointer in poisson_residual");
+  if (!workspace || workspace_bytes < spinn2d_poisson_residual_workspace_bytes(N))
+    return fail(SPINN_E_WORKSPACE, "residual workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = ceil_div_i(N, 256 * 4);
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  float* lpart = (float*)workspace;
+  poisson_residual_kernel<<<blocks, 256, 0, s>>>(N, (float)(1.0 / n_total), x, y, jets, scale, amp, kx,
+                                                 ky, f0, gjets, lpart);
+  LAUNCH_CHECK("poisson_residual_kernel");
+  add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
+  LAUNCH_CHECK("add_partials_kernel");
+  return SPINN_OK;
+}
+
+int spinn_microbench(int which, int iters, int blocks, int threads, float* sink, double* ops,
+                     void* stream) {
+  if (which < 0 || which > 3 || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256 || !sink)
+    return fail(SPINN_E_BADARG, "bad microbench arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const double lanes = (double)blocks * threads * iters;
+  switch (which) {
+    case 0: microbench_kernel<0><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
+    case 1: microbench_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
+    case 2: microbench_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
+    default: microbench_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 4 * 28; break;
+  }
+  LAUNCH_CHECK("microbench_kernel");
+  return SPINN_OK;
+}
+
+}  // extern "C"

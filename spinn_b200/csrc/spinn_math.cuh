@@ -1,0 +1,428 @@
+// spinn_math.cuh -- per-(point,node) arithmetic of the SPINN hot path.
+//
+// Everything here is __host__ __device__ so that tests/hostcheck can run the very
+// same formulas on the CPU against the oracle before GPU time is spent; the
+// product only ever calls them from the CUDA kernels in spinn_kernels.cu.
+//
+// Reference semantics being reproduced (paths relative to /root/reference):
+//   shift/scale layer   code/spinn2d.py:130-135, code/spinn1d.py:110-112
+//   gaussian            code/spinn2d.py:191-192, code/spinn1d.py:176-177
+//   softplus-hat        code/spinn2d.py:195-205, code/spinn1d.py:180-189
+//   jets via autograd   code/pde2d_base.py:46-62, code/ode_base.py:32-42
+// The derivatives are analytic here (closed forms).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SP_HD __host__ __device__ __forceinline__
+#else
+#define SP_HD inline
+#endif
+
+namespace spinn {
+
+enum Kind { GAUSSIAN = 0, SOFTPLUS = 1 };
+
+// ---- constants -------------------------------------------------------------
+// Gaussian: phi = exp(-q/2) = 2^{-(xi'^2+eta'^2)} with xi' = sigma*(x-c)/h and
+// sigma^2 = log2(e)/2.  We carry t = xi'^2+eta'^2-2 sigma^2 and fold 2^{-2 sigma^2}=1/e
+// into the weights.
+constexpr float  SIG2_F   = 0.72134752044448170f;      // log2(e)/2
+constexpr double SIG2_D   = 0.72134752044448170368;
+constexpr double SIG_D    = 0.84932180028801904272;    // sqrt(log2(e)/2)
+constexpr double INV_E_D  = 0.36787944117144232160;    // exp(-1)
+constexpr float  LOG2E_F  = 1.4426950408889634f;
+constexpr float  LN2_F    = 0.69314718055994531f;
+
+// softplus-hat constants exactly as the reference builds them (fp32 tensors):
+//   k   = fl32(1 + 2*dim*ln 2)                 code/spinn2d.py:198, code/spinn1d.py:183
+//   fac = torch softplus_fp32(1) = 0x3FA818F5  code/spinn2d.py:199, code/spinn1d.py:184
+// EK = exp(k) and 1/fac evaluated in double from those fp32 values.
+constexpr double HAT_K1_D   = 2.386294364929199;        // fl32(1+2 ln2)
+constexpr double HAT_K2_D   = 3.7725887298583984;       // fl32(1+4 ln2)
+constexpr double HAT_FAC_D  = 1.31326162815094;         // 0x3FA818F5
+constexpr float  HAT_EK1_F  = 10.873127696930396f;      // exp(HAT_K1_D)
+constexpr float  HAT_EK2_F  = 43.492512937828440f;      // exp(HAT_K2_D)
+constexpr float  HAT_IFAC_F = (float)(1.0 / HAT_FAC_D);
+
+// ---- scalar fast-math primitives (MUFU on device, libm on host) -------------
+SP_HD float ex2f_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return exp2f(x);
+#endif
+}
+SP_HD float lg2f_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return log2f(x);
+#endif
+}
+SP_HD float rcpf_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
+// ---- packed f32x2 helpers (FFMA2/FADD2/FMUL2 on sm_100a) --------------------
+SP_HD float2 f2(float a, float b) { return make_float2(a, b); }
+SP_HD float2 f2dup(float a) { return make_float2(a, a); }
+SP_HD float2 f2fma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+SP_HD float2 f2mul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+SP_HD float2 f2add(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+SP_HD float2 f2ex2neg(float2 t) { return make_float2(ex2f_fast(-t.x), ex2f_fast(-t.y)); }
+
+// =============================================================================
+// FAST PATH: 2-D Gaussian, one output (K=1).  Two lanes of a float2 carry two
+// NODES in the forward pass (points live in registers, node records stream from
+// shared memory) and two POINTS in the backward pass (nodes live in registers,
+// point records stream from shared memory).
+// =============================================================================
+
+// Per-node derived parameters for the forward pass (built once per launch by the
+// pack kernel, fp64 intermediates):
+//   nc=-c, nd=-d, rp=sigma/h, w0=W/e, w1=-W*rt/e, w2=W*rt^2/e,  rt=1/(sigma*h).
+struct G2FwdNode { float nc, nd, rp, w0, w1, w2; };
+
+SP_HD G2FwdNode g2_fwd_node(float c, float d, float h, float W) {
+  double hh = (double)h;
+  double rt = 1.0 / (SIG_D * hh);
+  G2FwdNode n;
+  n.nc = -c; n.nd = -d;
+  n.rp = (float)(SIG_D / hh);
+  n.w0 = (float)((double)W * INV_E_D);
+  n.w1 = (float)(-(double)W * rt * INV_E_D);
+  n.w2 = (float)((double)W * rt * rt * INV_E_D);
+  return n;
+}
+
+// accumulators: u, ux, uy, uxx, uyy (, uxy); each lane = partial sum over one node parity
+template <bool MIXED>
+SP_HD void g2_fwd_pair(float2 x2, float2 y2, float2 nc, float2 nd, float2 rp,
+                       float2 w0, float2 w1, float2 w2, float2* acc) {
+  const float2 nsig2 = f2dup(-SIG2_F);
+  float2 X  = f2add(x2, nc);
+  float2 Y  = f2add(y2, nd);
+  float2 xi = f2mul(X, rp);
+  float2 et = f2mul(Y, rp);
+  float2 hx = f2fma(xi, xi, nsig2);
+  float2 hy = f2fma(et, et, nsig2);
+  float2 t  = f2add(hx, hy);
+  float2 E  = f2ex2neg(t);
+  acc[0] = f2fma(w0, E, acc[0]);
+  float2 g = f2mul(w1, E);
+  acc[1] = f2fma(g, xi, acc[1]);
+  acc[2] = f2fma(g, et, acc[2]);
+  float2 e = f2mul(w2, E);
+  acc[3] = f2fma(e, hx, acc[3]);
+  acc[4] = f2fma(e, hy, acc[4]);
+  if (MIXED) {
+    float2 xe = f2mul(xi, et);
+    acc[5] = f2fma(e, xe, acc[5]);
+  }
+}
+
+// Backward node constants (all duplicated into both lanes by the kernel):
+//   nc, nd, rp as above; nrt=-rt; rho=rt^2; nk1=-2 sigma^2 rt^2; k2p=sigma^2 rt.
+struct G2BwdNode { float nc, nd, rp, nrt, rho, nk1, k2p; };
+
+SP_HD G2BwdNode g2_bwd_node(float c, float d, float h) {
+  double hh = (double)h;
+  double rt = 1.0 / (SIG_D * hh);
+  G2BwdNode n;
+  n.nc = -c; n.nd = -d;
+  n.rp  = (float)(SIG_D / hh);
+  n.nrt = (float)(-rt);
+  n.rho = (float)(rt * rt);
+  n.nk1 = (float)(-2.0 * SIG2_D * rt * rt);
+  n.k2p = (float)(SIG2_D * rt);
+  return n;
+}
+
+// acc[0]=A_W, acc[1]=-A_c, acc[2]=-A_d, acc[3]=-A_h  (backward algebra)
+SP_HD void g2_bwd_pair(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, float2 g3, float2 g4,
+                       float2 nc, float2 nd, float2 rp, float2 nrt, float2 rho, float2 nk1,
+                       float2 k2p, float2* acc) {
+  const float2 nsig2 = f2dup(-SIG2_F);
+  float2 X  = f2add(x2, nc);
+  float2 Y  = f2add(y2, nd);
+  float2 xi = f2mul(X, rp);
+  float2 et = f2mul(Y, rp);
+  float2 hx = f2fma(xi, xi, nsig2);
+  float2 hy = f2fma(et, et, nsig2);
+  float2 t  = f2add(hx, hy);
+  float2 E  = f2ex2neg(t);
+  float2 a  = f2mul(g1, xi);
+  float2 b  = f2mul(g2, et);
+  float2 q  = f2mul(g3, hx);
+  q = f2fma(g4, hy, q);
+  float2 bp = f2fma(rho, q, g0);
+  float2 ab = f2add(a, b);
+  float2 PE = f2fma(nrt, ab, bp);
+  float2 bx = f2fma(nrt, b, bp);
+  bx = f2fma(nk1, g3, bx);
+  float2 m  = f2mul(g1, hx);
+  float2 ncx = f2mul(xi, bx);
+  ncx = f2fma(nrt, m, ncx);
+  float2 by = f2fma(nrt, a, bp);
+  by = f2fma(nk1, g4, by);
+  float2 m2 = f2mul(g2, hy);
+  float2 ncy = f2mul(et, by);
+  ncy = f2fma(nrt, m2, ncy);
+  float2 nhh = f2mul(xi, ncx);
+  nhh = f2fma(et, ncy, nhh);
+  nhh = f2fma(nk1, q, nhh);
+  nhh = f2fma(k2p, ab, nhh);
+  acc[0] = f2fma(E, PE, acc[0]);
+  acc[1] = f2fma(E, ncx, acc[1]);
+  acc[2] = f2fma(E, ncy, acc[2]);
+  acc[3] = f2fma(E, nhh, acc[3]);
+}
+
+// final per-node factors: dW = A_W/e, dc = W rt/e * (-A_c), dd likewise, dh = W rt/(e sigma) * (-A_h)
+SP_HD void g2_bwd_finish(float h, float W, float aW, float nAc, float nAd, float nAh,
+                         float* dW, float* dc, float* dd, float* dh) {
+  double rt = 1.0 / (SIG_D * (double)h);
+  double f  = (double)W * rt * INV_E_D;
+  *dW = (float)((double)aW * INV_E_D);
+  *dc = (float)(f * (double)nAc);
+  *dd = (float)(f * (double)nAd);
+  *dh = (float)(f / SIG_D * (double)nAh);
+}
+
+// number of jets / upstream-gradient slots per "level"
+//   2-D: level 0: u | 1: u,ux,uy | 2: u,ux,uy,uxx,uyy | 3: + uxy
+//   1-D: level 0: u | 1: u,ux    | 2: u,ux,uxx
+SP_HD constexpr int njets(int dim, int level) {
+  return dim == 2 ? (level == 0 ? 1 : level == 1 ? 3 : level == 2 ? 5 : 6)
+                  : (level == 0 ? 1 : level == 1 ? 2 : 3);
+}
+
+// =============================================================================
+// GENERIC PATH: kernel value and every partial derivative w.r.t. the point up to
+// third order, for one (point, node) pair, in plain (unscaled) variables.  Used
+// by the generic kernels (1-D, softplus-hat, K>1, partial jet levels, u_xy).
+// d[] layout 2-D: 0:phi 1:x 2:y 3:xx 4:yy 5:xy 6:xxx 7:xyy 8:xxy 9:yyy
+// d[] layout 1-D: 0:phi 1:x 2:xx 3:xxx
+// =============================================================================
+
+// log1p(w) for 0 <= w <= ~3 from s = w/(1+w):  log1p(w) = -log(1-s).
+// MUFU.LG2 has an ABSOLUTE error of ~2^-22 near 1, so small w takes the series.
+SP_HD float log1p_from_sig(float w, float s) {
+  // -log(1-s) = s + s^2/2 + ... ; s <= 0.2 on this branch, 9 terms -> < 1e-7 relative
+  float p = 1.0f / 9.0f;
+  p = fmaf(p, s, 1.0f / 8.0f);
+  p = fmaf(p, s, 1.0f / 7.0f);
+  p = fmaf(p, s, 1.0f / 6.0f);
+  p = fmaf(p, s, 1.0f / 5.0f);
+  p = fmaf(p, s, 1.0f / 4.0f);
+  p = fmaf(p, s, 1.0f / 3.0f);
+  p = fmaf(p, s, 1.0f / 2.0f);
+  p = fmaf(p, s, 1.0f);
+  float small = p * s;
+  float big = LN2_F * lg2f_fast(1.0f + w);
+  return (w < 0.25f) ? small : big;
+}
+
+// one coordinate of the hat: e = exp(-2|s|), A = 1+e
+struct HatAxis { float e, A, sgn; };
+SP_HD HatAxis hat_axis(float s) {
+  HatAxis a;
+  a.e = ex2f_fast(-2.0f * LOG2E_F * fabsf(s));
+  a.A = 1.0f + a.e;
+  a.sgn = (s < 0.0f) ? -1.0f : 1.0f;
+  return a;
+}
+
+template <int KIND, int ORDER>
+SP_HD void phi_derivs_2d(float X, float Y, float r, float* d) {
+  const float rho = r * r;
+  if (KIND == GAUSSIAN) {
+    float a = rho * X, b = rho * Y;
+    float q = fmaf(a, X, b * Y);
+    float p = ex2f_fast(-0.5f * LOG2E_F * q);
+    d[0] = p;
+    if (ORDER >= 1) { d[1] = -a * p; d[2] = -b * p; }
+    if (ORDER >= 2) {
+      float A2 = fmaf(a, a, -rho), B2 = fmaf(b, b, -rho);
+      d[3] = A2 * p; d[4] = B2 * p; d[5] = a * b * p;
+      if (ORDER >= 3) {
+        d[6] = a * (2.0f * rho - A2) * p;      // (3 rho a - a^3) = a (2 rho - (a^2-rho))
+        d[9] = b * (2.0f * rho - B2) * p;
+        d[7] = -a * B2 * p;
+        d[8] = -A2 * b * p;
+      }
+    }
+  } else {
+    HatAxis ax = hat_axis(X * r), ay = hat_axis(Y * r);
+    float AA = ax.A * ay.A;
+    float R = rcpf_fast(AA);
+    float w = HAT_EK2_F * (ax.e * ay.e) * (R * R);              // e^z
+    float inv1w = rcpf_fast(1.0f + w);
+    float sg = w * inv1w;                                       // sigmoid(z)
+    float S = log1p_from_sig(w, sg);
+    d[0] = S * HAT_IFAC_F;
+    if (ORDER >= 1) {
+      float iAx = ay.A * R, iAy = ax.A * R;                     // 1/Ax, 1/Ay
+      float Tx = ax.sgn * (1.0f - ax.e) * iAx;                  // tanh
+      float Ty = ay.sgn * (1.0f - ay.e) * iAy;
+      float zx = -2.0f * r * Tx, zy = -2.0f * r * Ty;
+      float sgF = sg * HAT_IFAC_F;
+      d[1] = sgF * zx; d[2] = sgF * zy;
+      if (ORDER >= 2) {
+        float Cx = 4.0f * ax.e * iAx * iAx;                     // sech^2 without cancellation
+        float Cy = 4.0f * ay.e * iAy * iAy;
+        float zxx = -2.0f * rho * Cx, zyy = -2.0f * rho * Cy;
+        float s1 = sgF * inv1w;                                 // sigma (1-sigma)/F
+        d[3] = fmaf(s1 * zx, zx, sgF * zxx);
+        d[4] = fmaf(s1 * zy, zy, sgF * zyy);
+        d[5] = s1 * zx * zy;
+        if (ORDER >= 3) {
+          float s2 = s1 * (inv1w - sg);                         // sigma1 (1-2 sigma)
+          float zxxx = -2.0f * zxx * r * Tx;                    // 4 r^3 T C
+          float zyyy = -2.0f * zyy * r * Ty;
+          d[6] = fmaf(s2 * zx * zx, zx, fmaf(3.0f * s1 * zx, zxx, sgF * zxxx));
+          d[9] = fmaf(s2 * zy * zy, zy, fmaf(3.0f * s1 * zy, zyy, sgF * zyyy));
+          d[7] = zx * fmaf(s2 * zy, zy, s1 * zyy);
+          d[8] = zy * fmaf(s2 * zx, zx, s1 * zxx);
+        }
+      }
+    }
+  }
+}
+
+template <int KIND, int ORDER>
+SP_HD void phi_derivs_1d(float X, float r, float* d) {
+  const float rho = r * r;
+  if (KIND == GAUSSIAN) {
+    float a = rho * X;
+    float p = ex2f_fast(-0.5f * LOG2E_F * a * X);
+    d[0] = p;
+    if (ORDER >= 1) d[1] = -a * p;
+    if (ORDER >= 2) {
+      float A2 = fmaf(a, a, -rho);
+      d[2] = A2 * p;
+      if (ORDER >= 3) d[3] = a * (2.0f * rho - A2) * p;
+    }
+  } else {
+    HatAxis ax = hat_axis(X * r);
+    float iA = rcpf_fast(ax.A);
+    float w = HAT_EK1_F * ax.e * iA * iA;
+    float inv1w = rcpf_fast(1.0f + w);
+    float sg = w * inv1w;
+    float S = log1p_from_sig(w, sg);
+    d[0] = S * HAT_IFAC_F;
+    if (ORDER >= 1) {
+      float T = ax.sgn * (1.0f - ax.e) * iA;
+      float zx = -2.0f * r * T;
+      float sgF = sg * HAT_IFAC_F;
+      d[1] = sgF * zx;
+      if (ORDER >= 2) {
+        float C = 4.0f * ax.e * iA * iA;
+        float zxx = -2.0f * rho * C;
+        float s1 = sgF * inv1w;
+        d[2] = fmaf(s1 * zx, zx, sgF * zxx);
+        if (ORDER >= 3) {
+          float s2 = s1 * (inv1w - sg);
+          float zxxx = -2.0f * zxx * r * T;
+          d[3] = fmaf(s2 * zx * zx, zx, fmaf(3.0f * s1 * zx, zxx, sgF * zxxx));
+        }
+      }
+    }
+  }
+}
+
+
+// ---- generic per-pair accumulation (shared by the kernels and tests/hostcheck) ----
+// forward: acc[a][k] += W_k * phi_a
+template <int DIM, int KIND, int K, int LEVEL>
+SP_HD void generic_fwd_pair(float X, float Y, float r, const float* Wk, float (*acc)[K]) {
+  constexpr int NJ = njets(DIM, LEVEL);
+  constexpr int ORDER = LEVEL >= 2 ? 2 : LEVEL;
+  float d[10];
+  if (DIM == 2) phi_derivs_2d<KIND, ORDER>(X, Y, r, d);
+  else phi_derivs_1d<KIND, ORDER>(X, r, d);
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) acc[a][k] = fmaf(Wk[k], d[a], acc[a][k]);
+}
+
+// backward: acc rows 0 dc, (1 dd), DIM dh, DIM+1+k dW_k; g[(a*K+k)*gstride] upstream grads.
+// Kernel-agnostic: d/dc = -d/dx, and Euler scaling for d/dh.
+template <int DIM, int KIND, int K, int LEVEL>
+SP_HD void generic_bwd_pair(float X, float Y, float r, const float* Wk, const float* g, int gstride,
+                            float* acc) {
+  constexpr int NG = njets(DIM, LEVEL);
+  constexpr int ORDER = (LEVEL + 1) > 3 ? 3 : (LEVEL + 1);
+  float d[10];
+  if (DIM == 2) phi_derivs_2d<KIND, ORDER>(X, Y, r, d);
+  else phi_derivs_1d<KIND, ORDER>(X, r, d);
+  float G[NG];
+#pragma unroll
+  for (int a = 0; a < NG; ++a) G[a] = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < NG; ++a) {
+      const float gv = g[(a * K + k) * gstride];
+      s = fmaf(gv, d[a], s);
+      G[a] = fmaf(Wk[k], gv, G[a]);
+    }
+    acc[DIM + 1 + k] += s;
+  }
+  if (DIM == 2) {
+    // mdc, mdd hold -dc_ij, -dd_ij
+    float mdc = G[0] * d[1], mdd = G[0] * d[2], ord = 0.f;
+    if (NG >= 3) {
+      mdc = fmaf(G[1 % NG], d[3], fmaf(G[2 % NG], d[5], mdc));
+      mdd = fmaf(G[1 % NG], d[5], fmaf(G[2 % NG], d[4], mdd));
+      ord = fmaf(G[1 % NG], d[1], G[2 % NG] * d[2]);
+    }
+    if (NG >= 5) {
+      mdc = fmaf(G[3 % NG], d[6], fmaf(G[4 % NG], d[7], mdc));
+      mdd = fmaf(G[3 % NG], d[8], fmaf(G[4 % NG], d[9], mdd));
+      ord = fmaf(2.f * G[3 % NG], d[3], fmaf(2.f * G[4 % NG], d[4], ord));
+    }
+    if (NG >= 6) {
+      mdc = fmaf(G[5 % NG], d[8], mdc);
+      mdd = fmaf(G[5 % NG], d[7], mdd);
+      ord = fmaf(2.f * G[5 % NG], d[5], ord);
+    }
+    acc[0] -= mdc;
+    acc[1] -= mdd;
+    acc[2] -= r * fmaf(X, mdc, fmaf(Y, mdd, ord));
+  } else {
+    float mdc = G[0] * d[1], ord = 0.f;
+    if (NG >= 2) { mdc = fmaf(G[1 % NG], d[2], mdc); ord = G[1 % NG] * d[1]; }
+    if (NG >= 3) { mdc = fmaf(G[2 % NG], d[3], mdc); ord = fmaf(2.f * G[2 % NG], d[2], ord); }
+    acc[0] -= mdc;
+    acc[1] -= r * fmaf(X, mdc, ord);
+  }
+}
+
+}  // namespace spinn

@@ -1,0 +1,240 @@
+"""PyTorch custom ops over the C ABI: fused SPINN jets forward / backward.
+
+``fused_jets`` replaces, for one call of the network, what the reference does with
+a dense forward (code/spinn2d.py:169-179, code/spinn1d.py:147-156) followed by
+three nested ``torch.autograd.grad`` calls in the problem class
+(code/pde2d_base.py:46-62, code/ode_base.py:32-42): it returns u and its analytic
+spatial derivatives, and its autograd backward returns the gradients w.r.t.
+centres, widths, weights and bias that ``loss.backward()`` (code/common.py:242-248)
+would produce.
+
+``attach_tower`` makes those precomputed jets visible to UNCHANGED problem code:
+the problem class still calls ``ag.grad(u, (xs, ys), ..., create_graph=True)``
+twice; the tower's custom backward hands it the precomputed ``u_x``/``u_xx``...
+instead of re-differentiating an (N, M) graph.
+
+There is no CPU path: inputs must be CUDA fp32 tensors and the native library
+must be loadable, otherwise an exception is raised.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+GAUSSIAN = 0
+SOFTPLUS = 1
+
+_NJETS = {(2, 0): 1, (2, 1): 3, (2, 2): 5, (2, 3): 6, (1, 0): 1, (1, 1): 2, (1, 2): 3}
+MAX_K = 4
+
+
+def num_jets(dim, level):
+    return _NJETS[(dim, level)]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class CudaBackend:
+    """Thin marshalling layer: torch tensors -> raw device pointers -> C ABI."""
+
+    name = "cuda"
+
+    @staticmethod
+    def _check(*tensors):
+        dev = None
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise _cabi.SpinnNativeError(
+                    "spinn_b200 fused ops need CUDA tensors (no CPU fallback); got device "
+                    f"{t.device}. Run with --gpu / common.device('cuda').")
+            if t.dtype != torch.float32:
+                raise TypeError(f"spinn_b200 fused ops are fp32 (reference common.py:28); got {t.dtype}")
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise ValueError("all tensors must live on the same CUDA device")
+        return dev
+
+    def forward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
+        lib = _cabi.load()
+        dev = self._check(x, y, xf, yf, xfix, yfix, h, W, b)
+        N = x.numel()
+        Mf, Mx = xf.numel(), xfix.numel()
+        K = W.shape[0]
+        nj = num_jets(dim, level)
+        with torch.cuda.device(dev):
+            jets = torch.empty((nj, N, K), dtype=torch.float32, device=dev)
+            if N == 0:
+                return jets
+            if dim == 2:
+                nbytes = lib.spinn2d_fwd_workspace_bytes(N, Mf + Mx, K)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                rc = lib.spinn2d_jets_fwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(y), _ptr(xf), _ptr(yf),
+                                          _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1), _ptr(W),
+                                          _ptr(b), _ptr(jets), _ptr(ws), nbytes, _stream())
+            else:
+                nbytes = lib.spinn1d_fwd_workspace_bytes(N, Mf + Mx, K)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                rc = lib.spinn1d_jets_fwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(xf), _ptr(xfix), _ptr(h),
+                                          int(h.numel() == 1), _ptr(W), _ptr(b), _ptr(jets), _ptr(ws),
+                                          nbytes, _stream())
+        _cabi.check(rc, f"spinn{dim}d_jets_fwd")
+        return jets
+
+    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias):
+        lib = _cabi.load()
+        dev = self._check(x, y, xf, yf, xfix, yfix, h, W, gj)
+        N = x.numel()
+        Mf, Mx = xf.numel(), xfix.numel()
+        M = Mf + Mx
+        K = W.shape[0]
+        with torch.cuda.device(dev):
+            d_xc = torch.empty(Mf, dtype=torch.float32, device=dev)
+            d_yc = torch.empty(Mf, dtype=torch.float32, device=dev) if dim == 2 else None
+            d_h = torch.empty(h.numel(), dtype=torch.float32, device=dev)
+            d_W = torch.empty((K, M), dtype=torch.float32, device=dev)
+            d_b = torch.empty(K, dtype=torch.float32, device=dev) if want_bias else None
+            if dim == 2:
+                nbytes = lib.spinn2d_bwd_workspace_bytes(N, M, K)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                rc = lib.spinn2d_jets_bwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(y), _ptr(xf), _ptr(yf),
+                                          _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1), _ptr(W),
+                                          _ptr(gj), _ptr(d_xc), _ptr(d_yc), _ptr(d_h), _ptr(d_W), _ptr(d_b),
+                                          _ptr(ws), nbytes, _stream())
+            else:
+                nbytes = lib.spinn1d_bwd_workspace_bytes(N, M, K)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                rc = lib.spinn1d_jets_bwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(xf), _ptr(xfix), _ptr(h),
+                                          int(h.numel() == 1), _ptr(W), _ptr(gj), _ptr(d_xc), _ptr(d_h),
+                                          _ptr(d_W), _ptr(d_b), _ptr(ws), nbytes, _stream())
+        _cabi.check(rc, f"spinn{dim}d_jets_bwd")
+        return d_xc, d_yc, d_h, d_W, d_b
+
+
+_BACKEND = CudaBackend()
+
+
+def set_backend(backend):
+    """Test hook: tests/ inject an oracle-backed stand-in to exercise the host logic
+    (tower, plug-in surface) in the GPU-less build container.  Product code never
+    calls this."""
+    global _BACKEND
+    prev = _BACKEND
+    _BACKEND = backend
+    return prev
+
+
+def _level_for(dim, last_index):
+    """Smallest level whose upstream-gradient slots cover jet index `last_index`."""
+    for level in range(0, 4 if dim == 2 else 3):
+        if num_jets(dim, level) > last_index:
+            return level
+    raise ValueError(last_index)
+
+
+class _FusedJets(torch.autograd.Function):
+    """jets = F(x, y; centres, widths, weights).  Outputs: one (N, K) tensor per jet.
+
+    x, y are treated as constants here (callers pass detached tensors): the
+    spatial derivatives ARE the outputs; the tower below wires them to autograd."""
+
+    @staticmethod
+    def forward(ctx, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
+        hk = h.reshape(-1)
+        jets = _BACKEND.forward(dim, kind, level, x, y, xf, yf, xfix, yfix, hk, W, b)
+        ctx.meta = (dim, kind, level)
+        ctx.h_shape = h.shape
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, y, xf, yf, xfix, yfix, h, W)
+        ctx.set_materialize_grads(False)
+        return tuple(jets.unbind(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        dim, kind, level = ctx.meta
+        x, y, xf, yf, xfix, yfix, h, W = ctx.saved_tensors
+        present = [i for i, g in enumerate(gs) if g is not None]
+        if not present:
+            return (None,) * 12
+        lv = _level_for(dim, present[-1])
+        ng = num_jets(dim, lv)
+        N, K = x.numel(), W.shape[0]
+        gj = torch.zeros((ng, N, K), dtype=torch.float32, device=x.device)
+        for i in present:
+            gj[i].copy_(gs[i].reshape(N, K))
+        d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward(
+            dim, kind, lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias)
+        return (None, None, None, None, None, d_xc, d_yc, None, None,
+                d_h.reshape(ctx.h_shape), d_W, d_b)
+
+
+def fused_jets(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
+    """Tuple of jets, each (N, K).  2-D order u,ux,uy,uxx,uyy[,uxy]; 1-D u,ux,uxx."""
+    return _FusedJets.apply(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b)
+
+
+class _Attach(torch.autograd.Function):
+    """out = v, but with DECLARED derivatives d out/dx = vx, d out/dy = vy.
+
+    backward(g) = (g -> v, sum_k g*vx -> x, sum_k g*vy -> y); it is written with
+    differentiable torch ops on saved inputs, so ``create_graph=True`` keeps the
+    dependence on vx, vy (needed for the second ``ag.grad`` and for
+    ``loss.backward()`` to reach the fused op)."""
+
+    @staticmethod
+    def forward(ctx, v, x, y, vx, vy):
+        ctx.save_for_backward(vx, vy)
+        ctx.has_y = y is not None
+        return v.view_as(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        vx, vy = ctx.saved_tensors
+        gx = g * vx
+        if gx.dim() > 1:
+            gx = gx.sum(-1)
+        gy = None
+        if ctx.has_y:
+            gy = g * vy
+            if gy.dim() > 1:
+                gy = gy.sum(-1)
+        return g, gx, gy, None, None
+
+
+def attach_tower_2d(x, y, u, ux, uy, uxx, uyy, uxy):
+    """(N,K) jets -> u' such that the reference's ``_compute_derivatives``
+    (code/pde2d_base.py:46-62) recovers ux, uy, uxx, uyy (and uxy) from it."""
+    ux_ = _Attach.apply(ux, x, y, uxx, uxy)
+    uy_ = _Attach.apply(uy, x, y, uxy, uyy)
+    return _Attach.apply(u, x, y, ux_, uy_)
+
+
+def attach_tower_1d(x, u, ux, uxx):
+    """1-D twin for ``BasicODE._compute_derivatives`` (code/ode_base.py:32-42)."""
+    ux_ = _Attach1.apply(ux, x, uxx)
+    return _Attach1.apply(u, x, ux_)
+
+
+class _Attach1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, x, vx):
+        ctx.save_for_backward(vx)
+        return v.view_as(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        (vx,) = ctx.saved_tensors
+        gx = g * vx
+        if gx.dim() > 1:
+            gx = gx.sum(-1)
+        return g, gx, None

@@ -35,3 +35,52 @@ def maxnorm_err(new, ref):
     if scale == 0.0:
         return float(np.max(np.abs(new))) if new.size else 0.0
     return float(np.max(np.abs(new - ref)) / scale)
+
+
+# --------------------------------------------------------------------------- #
+# Oracle-backed stand-in for spinn_b200.ops.CudaBackend (CPU tests of host logic)
+# --------------------------------------------------------------------------- #
+class OracleBackend:
+    """Implements the backend protocol of spinn_b200.ops with oracle/closed_form.py.
+    TEST ONLY: lets the tower / plug-in surface / problem classes run in the
+    GPU-less build container.  Injected with ops.set_backend()."""
+
+    name = "oracle"
+
+    def __init__(self):
+        self.calls = {"forward": 0, "backward": 0}
+
+    @staticmethod
+    def _np(t):
+        return None if t is None else t.detach().cpu().numpy().astype(np.float64)
+
+    def forward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
+        import torch
+        from oracle import closed_form as cf
+        self.calls["forward"] += 1
+        nj = {(2, 0): 1, (2, 1): 3, (2, 2): 5, (2, 3): 6, (1, 0): 1, (1, 1): 2, (1, 2): 3}[(dim, level)]
+        n = self._np
+        if dim == 2:
+            J = cf.jets2d(kind, n(x), n(y), np.concatenate([n(xf), n(xfix)]),
+                          np.concatenate([n(yf), n(yfix)]), n(h), n(W), n(b))
+        else:
+            J = cf.jets1d(kind, n(x), np.concatenate([n(xf), n(xfix)]), n(h), n(W), n(b))
+        return torch.tensor(J[:nj], dtype=torch.float32, device=x.device)
+
+    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias):
+        import torch
+        from oracle import closed_form as cf
+        self.calls["backward"] += 1
+        n = self._np
+        g = n(gj)
+        full = 6 if dim == 2 else 3
+        if g.shape[0] < full:
+            g = np.concatenate([g, np.zeros((full - g.shape[0],) + g.shape[1:])], 0)
+        if dim == 2:
+            G = cf.grads2d(kind, n(x), n(y), np.concatenate([n(xf), n(xfix)]),
+                           np.concatenate([n(yf), n(yfix)]), n(h), n(W), g, n_free=xf.numel())
+        else:
+            G = cf.grads1d(kind, n(x), np.concatenate([n(xf), n(xfix)]), n(h), n(W), g, n_free=xf.numel())
+        t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32, device=x.device)
+        return (t(G["d_xc"]), t(G["d_yc"]) if dim == 2 else None, t(G["d_h"]), t(G["d_W"]),
+                t(G["d_b"]) if want_bias else None)

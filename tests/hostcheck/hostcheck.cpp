@@ -1,0 +1,134 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE ONLY (never loaded by the spinn_b200 package).
+// Runs the per-(point,node) formulas of spinn_b200/csrc/spinn_math.cuh on the CPU,
+// with the same loop structure as the CUDA kernels (node pairs / point pairs in the
+// two lanes of a float2, two-level accumulation), so that the algebra can be checked
+// against the oracle in the build container, which has no GPU.
+#include "../../spinn_b200/csrc/spinn_math.cuh"
+#include <vector>
+
+using namespace spinn;
+
+extern "C" {
+
+// fast forward emulation: jets [6][N]
+void hc_g2_fwd(int N, int M, const float* x, const float* y, const float* c, const float* d,
+               const float* h, const float* W, float bias, float* jets) {
+  int npairs = (M + 1) / 2;
+  std::vector<G2FwdNode> nodes(2 * npairs);
+  for (int j = 0; j < 2 * npairs; ++j)
+    nodes[j] = j < M ? g2_fwd_node(c[j], d[j], h[j], W[j]) : g2_fwd_node(0.f, 0.f, 1.f, 0.f);
+  for (int i = 0; i < N; ++i) {
+    float2 acc[6];
+    for (int a = 0; a < 6; ++a) acc[a] = f2(0.f, 0.f);
+    for (int p = 0; p < npairs; ++p) {
+      const G2FwdNode &n0 = nodes[2 * p], &n1 = nodes[2 * p + 1];
+      g2_fwd_pair<true>(f2dup(x[i]), f2dup(y[i]), f2(n0.nc, n1.nc), f2(n0.nd, n1.nd), f2(n0.rp, n1.rp),
+                        f2(n0.w0, n1.w0), f2(n0.w1, n1.w1), f2(n0.w2, n1.w2), acc);
+    }
+    for (int a = 0; a < 6; ++a) jets[(size_t)a * N + i] = acc[a].x + acc[a].y + (a == 0 ? bias : 0.f);
+  }
+}
+
+// fast backward emulation: g [5][N]; outputs dc, dd, dh, dW [M]
+void hc_g2_bwd(int N, int M, const float* x, const float* y, const float* g, const float* c,
+               const float* d, const float* h, const float* W, float* dc, float* dd, float* dh,
+               float* dW) {
+  int N2 = (N + 1) / 2;
+  for (int j = 0; j < M; ++j) {
+    G2BwdNode n = g2_bwd_node(c[j], d[j], h[j]);
+    float tot[4] = {0, 0, 0, 0};
+    for (int t0 = 0; t0 < N2; t0 += 256) {
+      float2 acc[4];
+      for (int a = 0; a < 4; ++a) acc[a] = f2(0.f, 0.f);
+      int t1 = t0 + 256 < N2 ? t0 + 256 : N2;
+      for (int p = t0; p < t1; ++p) {
+        int i0 = 2 * p, i1 = 2 * p + 1;
+        bool v = i1 < N;
+        float2 gg[5];
+        for (int a = 0; a < 5; ++a) gg[a] = f2(g[(size_t)a * N + i0], v ? g[(size_t)a * N + i1] : 0.f);
+        g2_bwd_pair(f2(x[i0], v ? x[i1] : x[i0]), f2(y[i0], v ? y[i1] : y[i0]), gg[0], gg[1], gg[2],
+                    gg[3], gg[4], f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), f2dup(n.nrt), f2dup(n.rho),
+                    f2dup(n.nk1), f2dup(n.k2p), acc);
+      }
+      for (int a = 0; a < 4; ++a) tot[a] += acc[a].x + acc[a].y;
+    }
+    g2_bwd_finish(h[j], W[j], tot[0], tot[1], tot[2], tot[3], &dW[j], &dc[j], &dd[j], &dh[j]);
+  }
+}
+
+}  // extern "C"
+
+template <int DIM, int KIND, int K, int LEVEL>
+static void gen_fwd(int N, int M, const float* x, const float* y, const float* c, const float* d,
+                    const float* h, const float* W, const float* bias, float* jets) {
+  constexpr int NJ = njets(DIM, LEVEL);
+  for (int i = 0; i < N; ++i) {
+    float acc[NJ][K];
+    for (int a = 0; a < NJ; ++a) for (int k = 0; k < K; ++k) acc[a][k] = 0.f;
+    for (int j = 0; j < M; ++j) {
+      float Wk[K];
+      for (int k = 0; k < K; ++k) Wk[k] = W[(size_t)k * M + j];
+      generic_fwd_pair<DIM, KIND, K, LEVEL>(x[i] - c[j], DIM == 2 ? y[i] - d[j] : 0.f, 1.0f / h[j], Wk, acc);
+    }
+    for (int a = 0; a < NJ; ++a) for (int k = 0; k < K; ++k)
+      jets[((size_t)a * N + i) * K + k] = acc[a][k] + ((a == 0 && bias) ? bias[k] : 0.f);
+  }
+}
+
+template <int DIM, int KIND, int K, int LEVEL>
+static void gen_bwd(int N, int M, const float* x, const float* y, const float* g, const float* c,
+                    const float* d, const float* h, const float* W, float* out /*[NACC][M]*/) {
+  constexpr int NG = njets(DIM, LEVEL);
+  constexpr int NACC = DIM + 1 + K;
+  std::vector<float> gp(NG * K);
+  for (int j = 0; j < M; ++j) {
+    float acc[NACC];
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+    float Wk[K];
+    for (int k = 0; k < K; ++k) Wk[k] = W[(size_t)k * M + j];
+    for (int i = 0; i < N; ++i) {
+      for (int a = 0; a < NG; ++a) for (int k = 0; k < K; ++k) gp[a * K + k] = g[((size_t)a * N + i) * K + k];
+      generic_bwd_pair<DIM, KIND, K, LEVEL>(x[i] - c[j], DIM == 2 ? y[i] - d[j] : 0.f, 1.0f / h[j], Wk,
+                                            gp.data(), 1, acc);
+    }
+    for (int a = 0; a < NACC; ++a) out[(size_t)a * M + j] = acc[a];
+  }
+}
+
+extern "C" {
+
+#define HC_DISPATCH_LEVEL(FN, DIM, KIND, K, ...)                                     \
+  switch (level) {                                                                   \
+    case 0: FN<DIM, KIND, K, 0>(__VA_ARGS__); break;                                 \
+    case 1: FN<DIM, KIND, K, 1>(__VA_ARGS__); break;                                 \
+    case 2: FN<DIM, KIND, K, 2>(__VA_ARGS__); break;                                 \
+    default: FN<DIM, KIND, K, (DIM == 2 ? 3 : 2)>(__VA_ARGS__); break;               \
+  }
+#define HC_DISPATCH_K(FN, DIM, KIND, ...)                                            \
+  switch (K) {                                                                       \
+    case 1: HC_DISPATCH_LEVEL(FN, DIM, KIND, 1, __VA_ARGS__) break;                  \
+    case 2: HC_DISPATCH_LEVEL(FN, DIM, KIND, 2, __VA_ARGS__) break;                  \
+    default: HC_DISPATCH_LEVEL(FN, DIM, KIND, 3, __VA_ARGS__) break;                 \
+  }
+#define HC_DISPATCH(FN, ...)                                                         \
+  if (dim == 2) {                                                                    \
+    if (kind == 0) { HC_DISPATCH_K(FN, 2, GAUSSIAN, __VA_ARGS__) }                   \
+    else { HC_DISPATCH_K(FN, 2, SOFTPLUS, __VA_ARGS__) }                             \
+  } else {                                                                           \
+    if (kind == 0) { HC_DISPATCH_K(FN, 1, GAUSSIAN, __VA_ARGS__) }                   \
+    else { HC_DISPATCH_K(FN, 1, SOFTPLUS, __VA_ARGS__) }                             \
+  }
+
+void hc_generic_fwd(int dim, int kind, int level, int K, int N, int M, const float* x, const float* y,
+                    const float* c, const float* d, const float* h, const float* W, const float* bias,
+                    float* jets) {
+  HC_DISPATCH(gen_fwd, N, M, x, y, c, d, h, W, bias, jets)
+}
+
+void hc_generic_bwd(int dim, int kind, int level, int K, int N, int M, const float* x, const float* y,
+                    const float* g, const float* c, const float* d, const float* h, const float* W,
+                    float* out) {
+  HC_DISPATCH(gen_bwd, N, M, x, y, g, c, d, h, W, out)
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""CPU check of the device formulas in spinn_b200/csrc/spinn_math.cuh.
+
+tests/hostcheck/hostcheck.cpp compiles that header for the host (g++) and walks
+the same loops as the CUDA kernels; results are compared with the fp64 oracle on
+the reference-generated golden cases.  This is test scaffolding: it validates the
+ALGEBRA here (no GPU in the build container); the -m gpu tests validate the
+kernels themselves through the C ABI.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import closed_form as cf
+from helpers import OP_CASES_1D, OP_CASES_2D, load_case, mixed_err
+
+HC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(FP) if a is not None else None
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC_DIR, "libhostcheck.so")
+    src = os.path.join(HC_DIR, "hostcheck.cpp")
+    hdr = os.path.join(HC_DIR, "..", "..", "spinn_b200", "csrc", "spinn_math.cuh")
+    stale = (not os.path.exists(so)) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so)
+    if stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+                               "-I/usr/local/cuda/include", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+TOL = 2e-5   # fp32 arithmetic vs fp64 oracle, mixed relative/absolute metric (helpers.mixed_err)
+
+
+def _nodes2d(c):
+    xc = f32(np.concatenate([c["xf"], c["xfix"]]))
+    yc = f32(np.concatenate([c["yf"], c["yfix"]]))
+    h = f32(c["h"])
+    if h.size == 1:
+        h = f32(np.full(xc.size, h[0]))
+    return xc, yc, h
+
+
+@pytest.mark.parametrize("name", [n for n in OP_CASES_2D if n.startswith("g2d") and load_case(n)["K"] == 1])
+def test_fast_gaussian_forward_and_backward(hc, name):
+    c = load_case(name)
+    xc, yc, h = _nodes2d(c)
+    x, y, W, b = f32(c["x"]), f32(c["y"]), f32(c["W"]).reshape(-1), f32(c["b"])
+    N, M = x.size, xc.size
+    jets = np.zeros((6, N), np.float32)
+    hc.hc_g2_fwd(N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), ctypes.c_float(b[0]), _ptr(jets))
+    ref = cf.jets2d("gaussian", x, y, xc, yc, h, W.reshape(1, -1), b)[:, :, 0]
+    for a in range(6):
+        assert mixed_err(jets[a], ref[a]) < TOL, (name, a)
+    g = f32(c["gjets"][:5, :, 0])
+    dc, dd, dh, dW = (np.zeros(M, np.float32) for _ in range(4))
+    hc.hc_g2_bwd(N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W),
+                 _ptr(dc), _ptr(dd), _ptr(dh), _ptr(dW))
+    G = cf.grads2d("gaussian", x, y, xc, yc, h, W.reshape(1, -1), g[:, :, None])
+    assert mixed_err(dc, G["d_xc"]) < TOL
+    assert mixed_err(dd, G["d_yc"]) < TOL
+    assert mixed_err(dh, G["d_h"]) < TOL
+    assert mixed_err(dW, G["d_W"][0]) < TOL
+
+
+@pytest.mark.parametrize("name", OP_CASES_2D)
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_generic_2d(hc, name, level):
+    c = load_case(name)
+    K = int(c["K"])
+    kind = cf.kind_id(c["kind"])
+    xc, yc, h = _nodes2d(c)
+    x, y, W, b = f32(c["x"]), f32(c["y"]), f32(c["W"]), f32(c["b"])
+    N, M = x.size, xc.size
+    nj = (1, 3, 5, 6)[level]
+    jets = np.zeros((nj, N, K), np.float32)
+    hc.hc_generic_fwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
+    ref = cf.jets2d(kind, x, y, xc, yc, h, W, b)
+    for a in range(nj):
+        assert mixed_err(jets[a], ref[a]) < TOL, (name, level, a)
+    g = f32(np.random.RandomState(5).randn(nj, N, K))
+    out = np.zeros((3 + K, M), np.float32)
+    hc.hc_generic_bwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(out))
+    g6 = np.zeros((6, N, K), np.float64)
+    g6[:nj] = g
+    G = cf.grads2d(kind, x, y, xc, yc, h, W, g6)
+    assert mixed_err(out[0], G["d_xc"]) < TOL
+    assert mixed_err(out[1], G["d_yc"]) < TOL
+    assert mixed_err(out[2], G["d_h"]) < TOL
+    assert mixed_err(out[3:], G["d_W"]) < TOL
+
+
+@pytest.mark.parametrize("name", OP_CASES_1D)
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_generic_1d(hc, name, level):
+    c = load_case(name)
+    K = int(c["K"])
+    kind = cf.kind_id(c["kind"])
+    xc = f32(np.concatenate([c["xf"], c["xfix"]]))
+    h = f32(c["h"])
+    x, W, b = f32(c["x"]), f32(c["W"]), f32(c["b"])
+    N, M = x.size, xc.size
+    nj = level + 1
+    jets = np.zeros((nj, N, K), np.float32)
+    hc.hc_generic_fwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(xc), None, _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
+    ref = cf.jets1d(kind, x, xc, h, W, b)
+    for a in range(nj):
+        assert mixed_err(jets[a], ref[a]) < TOL, (name, level, a)
+    g = f32(np.random.RandomState(6).randn(nj, N, K))
+    out = np.zeros((2 + K, M), np.float32)
+    hc.hc_generic_bwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(g), _ptr(xc), None, _ptr(h), _ptr(W), _ptr(out))
+    g3 = np.zeros((3, N, K), np.float64)
+    g3[:nj] = g
+    G = cf.grads1d(kind, x, xc, h, W, g3)
+    assert mixed_err(out[0], G["d_xc"]) < TOL
+    assert mixed_err(out[1], G["d_h"]) < TOL
+    assert mixed_err(out[2:], G["d_W"]) < TOL
