@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the SPINN hot path on B200: point-node evaluations/s of the fused
+residual forward+backward on the BASELINE 'synthetic scaled Poisson2D' workload
+(4 194 304 collocation points x 4096 nodes, Gaussian kernel, fp32), point-sharded over
+the GPUs of one box (strong scaling: the global point set is fixed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference's CPU algorithm (oracle port)
+
+One "step" = interior forward jets (u, ux, uy, uxx, uyy) -> residual/loss/upstream
+gradients -> backward to all node parameters -> one all-reduce of the packed gradient.
+`value` times it with inputs resident in HBM; `e2e` times the same quantity through
+the public plug-in API (SPINN2D.forward + the problem class's autograd recipe +
+loss.backward) with points coming from pinned host memory and the gradient+loss going
+back to the host every step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "point-node evals/sec for fused residual fwd+bwd"
+UNIT = "point-node evals/s"
+FLOP_PER_PAIR = 76.0          # 23 fwd + 13 recompute + 40 bwd
+FLOP_FWD, FLOP_BWD = 23.0, 53.0
+MUFU_PER_PAIR = 2.0
+SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--samples", type=int, default=4194304)
+    p.add_argument("--nodes", type=int, default=3600)
+    p.add_argument("--b-nodes", type=int, default=124)
+    p.add_argument("--kind", default="gaussian", choices=["gaussian", "softplus"])
+    p.add_argument("--cpu-chunk", type=int, default=16384)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's CPU algorithm (oracle port) -- cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup):
+    """Times oracle/torch_port.poisson_interior_step (dense (N,M) tensors + 3x autograd.grad +
+    backward: the reference's own algorithm, spinn2d.py:169-179 + pde2d_base.py:46-62 +
+    common.py:242-248) on a chunk of the same workload, all host threads."""
+    from oracle import torch_port as tp
+    from spinn_b200 import common, synthetic
+    common.device("cpu")
+    n_side = int(round(np.sqrt(args.cpu_chunk)))
+    pde, nn = synthetic.make_state(args.nodes, args.b_nodes, n_side * n_side, args.kind, device="cpu")
+    xs, ys = pde.p_samples
+    n = xs.numel()
+    l1, l2 = nn.layer1, nn.layer2
+    M = l1.n
+    kind = args.kind
+
+    def one():
+        for t in (xs, ys, l1.x, l1.y, l1.h, l2.weight, l2.bias):
+            t.grad = None
+        xc, yc = l1.centers()
+        return tp.poisson_interior_step(kind, xs, ys, xc, yc, l1.h, l2.weight, l2.bias, float(args.samples))
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return {"value": n * M * steps / dt, "ms_per_step": 1e3 * dt / steps, "points": n, "nodes": M,
+            "cores": torch.get_num_threads(), "nproc": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, args.warmup)
+    sample = (f"{r['points']} of {args.samples} points x {r['nodes']} nodes per step, dense eager fp32 "
+              f"fwd+3x autograd.grad+backward (oracle/torch_port.py)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "synthetic scaled Poisson2D: 4194304 collocation points x 4096 nodes "
+                               "(bounded CPU sample per step)", "kind": args.kind,
+                   "points_per_step": r["points"], "nodes": r["nodes"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def microbench_peaks(lib, dev):
+    """FP32 FMA and MUFU.EX2 issue rates measured on this GPU right now (lane-ops/s)."""
+    import ctypes
+    sink = torch.zeros(4, device=dev)
+    out = {}
+    s = torch.cuda.current_stream().cuda_stream
+    for which, name in ((0, "ffma"), (1, "ffma2"), (2, "ex2"), (3, "fwd_mix")):
+        ops = ctypes.c_double(0.0)
+        iters = 4096 if which != 2 else 1024
+        best = None
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            rc = lib.spinn_microbench(which, iters, SMS * 8, 256, sink.data_ptr(), ctypes.byref(ops), s)
+            e1.record()
+            torch.cuda.synchronize()
+            assert rc == 0
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[name] = ops.value / (best * 1e-3)
+    return out
+
+
+def run_ours(args):
+    from spinn_b200 import _cabi, common, distributed, synthetic
+    from spinn_b200.fused_step import PoissonInteriorStep
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the spinn_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU algorithm)")
+    rank, ws, local = distributed.init()
+    if ws != args.gpus:
+        if ws == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _cabi.load()
+    common.device(dev)
+
+    pde, nn = synthetic.make_state(args.nodes, args.b_nodes, args.samples, args.kind, device=dev)
+    xs_all, ys_all = (t.detach() for t in pde.p_samples)
+    N = xs_all.numel()
+    M = nn.layer1.n
+    lo, hi = distributed.shard_range(N, rank, ws)
+    xs, ys = xs_all[lo:hi].contiguous(), ys_all[lo:hi].contiguous()
+    del xs_all, ys_all
+    n_loc = hi - lo
+    step = PoissonInteriorStep(nn, xs, ys, n_total=N)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident timing ("value") ----
+    for _ in range(args.warmup):
+        step.run()
+    barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step.run()
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = N * M / (ms_step * 1e-3)
+    loss = float(step.pack.view("loss")[0])
+
+    # ---- per-kernel timing for the roofline (fwd, bwd incl. their tiny pack kernels) ----
+    def time_call(fn, reps=5):
+        best = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    l1, l2 = nn.layer1, nn.layer2
+    P = lambda t: None if t is None else t.data_ptr()
+    S = lambda: torch.cuda.current_stream().cuda_stream
+    hs = int(l1.h.numel() == 1)
+
+    def fwd_only():
+        rc = lib.spinn2d_jets_fwd(nn.kind, 2, n_loc, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y),
+                                  P(l1.xf), P(l1.yf), P(l1.h), hs, P(l2.weight), P(l2.bias), P(step.jets),
+                                  P(step.ws_f), step.ws_f.numel(), S())
+        assert rc == 0
+
+    def bwd_only():
+        p = step.pack
+        rc = lib.spinn2d_jets_bwd(nn.kind, 2, n_loc, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y),
+                                  P(l1.xf), P(l1.yf), P(l1.h), hs, P(l2.weight), P(step.gjets),
+                                  P(p.view("d_x")), P(p.view("d_y")), P(p.view("d_h")), P(p.view("d_W")),
+                                  P(p.view("d_b")), P(step.ws_b), step.ws_b.numel(), S())
+        assert rc == 0
+
+    ms_fwd = max_over_ranks(time_call(fwd_only))
+    ms_bwd = max_over_ranks(time_call(bwd_only))
+    pairs_loc = float(n_loc) * M
+
+    # ---- end to end through the public API, host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        xh = xs.cpu().pin_memory()
+        yh = ys.cpu().pin_memory()
+        pack = step.pack
+        out_host = torch.empty(pack.flat.numel(), dtype=torch.float32).pin_memory()
+        params = [l1.x, l1.y, l1.h, l2.weight, l2.bias]
+
+        def e2e_step():
+            x = xh.to(dev, non_blocking=True).requires_grad_(True)
+            y = yh.to(dev, non_blocking=True).requires_grad_(True)
+            for p_ in params:
+                p_.grad = None
+            u = nn(x, y)                                               # public plug-in call
+            u, ux, uy, uxx, uyy = pde._compute_derivatives(u, x, y)    # the problem class's ag.grad recipe
+            res = pde.pde(x, y, u, ux, uy, uxx, uyy)
+            lossv = (res ** 2).sum() / N
+            lossv.backward()
+            flat = pack.flat
+            flat.zero_()
+            pack.view("d_x").copy_(l1.x.grad)
+            pack.view("d_y").copy_(l1.y.grad)
+            pack.view("d_h").copy_(l1.h.grad.reshape(-1))
+            pack.view("d_W").copy_(l2.weight.grad.reshape(-1))
+            pack.view("d_b").copy_(l2.bias.grad)
+            pack.view("loss").copy_(lossv.detach().reshape(1))
+            pack.all_reduce()
+            out_host.copy_(flat, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(max(2, args.warmup)):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        for _ in range(args.steps):
+            e2e_step()
+        b.record()
+        barrier()
+        ms_e2e = max_over_ranks(a.elapsed_time(b)) / args.steps
+        e2e = {"value": N * M / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": 2 * 4 * n_loc, "d2h_bytes_per_step": pack.nbytes(),
+               "loss": float(out_host[pack.slices["loss"][0]]),
+               "api": "SPINN2D.forward -> RegularPDE._compute_derivatives -> pde() -> loss.backward()"}
+
+    if rank != 0:
+        if ws > 1:
+            dist.barrier()
+        return
+
+    peaks = microbench_peaks(lib, dev)
+    clocks = clk.summary()
+    nominal_fp32 = SMS * LANES * 2 * NOMINAL_MHZ * 1e6          # flop/s
+    measured_fp32 = 2.0 * max(peaks["ffma"], peaks["ffma2"])     # flop/s from lane-FMA/s
+    ach_bwd = pairs_loc * FLOP_BWD / (ms_bwd * 1e-3)
+    ach_fwd = pairs_loc * FLOP_FWD / (ms_fwd * 1e-3)
+    ach_step = N * M * FLOP_PER_PAIR / (ms_step * 1e-3) / ws
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hbm_bytes_step = 60.0 * n_loc + 64.0 * n_loc / 2 * 2          # jets/gjets/x/y + packed point records w+r
+    roofline = {
+        "bound": "fp32", "kernel": "g2k1_bwd_kernel<2>",
+        "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
+        "frac": ach_bwd / measured_fp32, "traffic": None,
+        "peak_source": "in-run FFMA/FFMA2 microbenchmark (spinn_microbench), lane-FMA/s x 2",
+        "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
+        "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR},
+        "kernels": {
+            "fwd": {"ms": ms_fwd, "tflops": ach_fwd / 1e12, "frac": ach_fwd / measured_fp32},
+            "bwd": {"ms": ms_bwd, "tflops": ach_bwd / 1e12, "frac": ach_bwd / measured_fp32},
+            "step": {"ms": ms_step, "tflops_per_gpu": ach_step / 1e12, "frac": ach_step / measured_fp32,
+                     "frac_of_nominal": ach_step / nominal_fp32},
+        },
+        "mufu": {"achieved_gops": pairs_loc * MUFU_PER_PAIR / ((ms_fwd + ms_bwd) * 1e-3) / 1e9,
+                 "peak_gops": peaks["ex2"] / 1e9,
+                 "frac": pairs_loc * MUFU_PER_PAIR / ((ms_fwd + ms_bwd) * 1e-3) / peaks["ex2"]},
+        "hbm": {"achieved_gbs": hbm_bytes_step / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": hbm_bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+        "microbench_lane_ops_per_s": peaks,
+    }
+
+    cpu_baseline = None
+    if ws == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args, steps=3, warmup=1)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                        "ms_per_sample_step": r["ms_per_step"],
+                        "sample": f"{r['points']} of {N} points x {r['nodes']} nodes, 3 reps after 1 warm-up, "
+                                  f"dense eager fp32 fwd+3x autograd.grad+backward (oracle/torch_port.py), "
+                                  f"{r['cores']} torch threads of {r['nproc']} cpus"}
+        common.device(dev)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic scaled Poisson2D: {N} collocation points x {M} nodes, "
+                               f"{args.kind} kernel, K=1, 5 jets (u,ux,uy,uxx,uyy), point-sharded over {ws} GPU(s)",
+                   "points": N, "nodes": M, "points_per_gpu": n_loc, "kind": args.kind,
+                   "l2_policy": "inputs larger than L2: per step x,y 8 B + jets 20 B + gjets 20 B + packed "
+                                "point records 32 B per point (>300 MB at 4M points vs 126 MB L2)",
+                   "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
+                                 if ws > 1 else "none (1 GPU)"},
+        "loss": loss, "train_step_ms": ms_step,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": PoissonInteriorStep.LAUNCHES * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.barrier()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    run_ours(args)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Fused interior step for the stock Poisson residual: forward jets -> residual/loss/
+upstream-gradient epilogue -> backward -> (all-reduce), all through the C ABI with
+preallocated buffers.  This is the throughput path the benchmark times; it computes
+exactly what ``RegularPDE.interior_loss`` + ``loss.backward()`` compute for
+``pde = scale*(u_xx + u_yy + amp*sin(kx x) sin(ky y) + f0)`` (reference
+code/pde2d_base.py:132-141, code/poisson2d_sine.py:16-18, code/poisson2d_irreg_dom.py:146-147).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _cabi
+from .distributed import GradPack
+from .ops import _ptr, _stream
+
+SINE = dict(scale=0.1, amp=20.0 * math.pi ** 2, kx=2.0 * math.pi, ky=4.0 * math.pi, f0=0.0)
+UNIT_SOURCE = dict(scale=1.0, amp=0.0, kx=0.0, ky=0.0, f0=1.0)
+
+
+class PoissonInteriorStep:
+    #: kernels of ours enqueued by one run(): pack_nodes(fwd), fwd, residual, add_partials,
+    #: pack_nodes(bwd), pack_points, bwd, bias_partial, finalize
+    LAUNCHES = 9
+
+    def __init__(self, nn, x, y, n_total=None, residual=SINE):
+        if nn.layer2.weight.shape[0] != 1:
+            raise ValueError("PoissonInteriorStep is for scalar problems (K=1)")
+        self.lib = _cabi.load()
+        self.nn = nn
+        self.x = x.detach().contiguous()
+        self.y = y.detach().contiguous()
+        self.N = self.x.numel()
+        self.n_total = float(self.N if n_total is None else n_total)
+        self.res = dict(residual)
+        l1, l2 = nn.layer1, nn.layer2
+        dev = self.x.device
+        self.Mf, self.Mx = l1.x.numel(), l1.xf.numel()
+        M = self.Mf + self.Mx
+        self.pack = GradPack(2, self.Mf, M, 1, l1.h.numel(), l2.bias is not None, dev)
+        self.jets = torch.empty((5, self.N), dtype=torch.float32, device=dev)
+        self.gjets = torch.empty((5, self.N), dtype=torch.float32, device=dev)
+        self.ws_f = torch.empty(self.lib.spinn2d_fwd_workspace_bytes(self.N, M, 1), dtype=torch.uint8, device=dev)
+        self.ws_b = torch.empty(self.lib.spinn2d_bwd_workspace_bytes(self.N, M, 1), dtype=torch.uint8, device=dev)
+        self.ws_r = torch.empty(self.lib.spinn2d_poisson_residual_workspace_bytes(self.N), dtype=torch.uint8, device=dev)
+
+    def run(self, all_reduce=True):
+        """Enqueue one interior fwd+bwd on the current stream.  Afterwards
+        ``self.pack.flat`` holds [grads | loss] (summed over ranks if all_reduce)."""
+        lib, nn = self.lib, self.nn
+        l1, l2 = nn.layer1, nn.layer2
+        s = _stream()
+        hs = int(l1.h.numel() == 1)
+        p = self.pack
+        p.view("loss").zero_()
+        rc = lib.spinn2d_jets_fwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
+                                  _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
+                                  _ptr(l2.weight), _ptr(l2.bias), _ptr(self.jets), _ptr(self.ws_f),
+                                  self.ws_f.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_fwd")
+        r = self.res
+        rc = lib.spinn2d_poisson_residual(self.N, self.n_total, _ptr(self.x), _ptr(self.y), _ptr(self.jets),
+                                          r["scale"], r["amp"], r["kx"], r["ky"], r["f0"], _ptr(self.gjets),
+                                          _ptr(p.view("loss")), _ptr(self.ws_r), self.ws_r.numel(), s)
+        _cabi.check(rc, "spinn2d_poisson_residual")
+        rc = lib.spinn2d_jets_bwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
+                                  _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
+                                  _ptr(l2.weight), _ptr(self.gjets), _ptr(p.view("d_x")), _ptr(p.view("d_y")),
+                                  _ptr(p.view("d_h")), _ptr(p.view("d_W")),
+                                  _ptr(p.view("d_b")) if p.has("d_b") else None,
+                                  _ptr(self.ws_b), self.ws_b.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_bwd")
+        if all_reduce:
+            p.all_reduce()
+        return p.flat
+
+    def assign_grads(self):
+        """Point the module's .grad at the (all-reduced) packed gradients."""
+        l1, l2, p = self.nn.layer1, self.nn.layer2, self.pack
+        l1.x.grad = p.view("d_x")
+        l1.y.grad = p.view("d_y")
+        l1.h.grad = p.view("d_h").reshape(l1.h.shape)
+        l2.weight.grad = p.view("d_W").reshape(l2.weight.shape)
+        if l2.bias is not None:
+            l2.bias.grad = p.view("d_b")
+        return p.view("loss")

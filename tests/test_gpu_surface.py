@@ -1,0 +1,111 @@
+"""GPU tests of the plug-in surface: the autograd tower over the real CUDA op, and the
+four BASELINE configurations driven through App.run(--gpu), compared step by step with
+loss histories recorded from the reference itself (tests/golden/traj_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_case, mixed_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _StubPDE:
+    def __init__(self, nodes, fixed, k):
+        self._n, self._f, self._k = nodes, fixed, k
+
+    def nodes(self):
+        return self._n
+
+    def fixed_nodes(self):
+        return self._f
+
+    def n_vars(self):
+        return self._k
+
+
+@pytest.fixture()
+def on_gpu():
+    from spinn_b200 import common, ops
+    assert isinstance(ops._BACKEND, ops.CudaBackend)
+    common.device("cuda")
+    yield
+    common.device("cpu")
+
+
+@pytest.mark.parametrize("name", ["g2d_k1", "s2d_k1", "g2d_k3", "s2d_k3", "g2d_nofixed", "g2d_fixed_h",
+                                  "g2d_one_point", "g2d_wide", "s2d_wide"])
+def test_tower_on_gpu_matches_reference_autograd(on_gpu, name):
+    from spinn_b200 import spinn2d
+    from spinn_b200.common import tensor
+    from spinn_b200.problems import derivs
+    c = load_case(name)
+    K = int(c["K"])
+    act = spinn2d.gaussian if c["kind"] == "gaussian" else spinn2d.SoftPlus()
+    nn = spinn2d.SPINN2D(_StubPDE((c["xf"], c["yf"]), (c["xfix"], c["yfix"]), K), act,
+                         fixed_h=c["h"].size == 1).to("cuda")
+    with torch.no_grad():
+        nn.layer1.x.copy_(tensor(c["xf"]))
+        nn.layer1.y.copy_(tensor(c["yf"]))
+        nn.layer1.h.copy_(tensor(c["h"]).reshape(nn.layer1.h.shape))
+        nn.layer2.weight.copy_(tensor(c["W"]))
+        nn.layer2.bias.copy_(tensor(c["b"]))
+    x = tensor(c["x"], requires_grad=True)
+    y = tensor(c["y"], requires_grad=True)
+    U = nn(x, y).reshape(x.numel(), K)
+    g = tensor(c["gjets"])
+    L = 0.0
+    for k in range(K):
+        got = torch.stack(derivs.jets_2d(U[:, k], x, y))
+        for a in range(5):
+            assert mixed_err(got[a].detach().cpu().numpy(), c["jets_f64"][a, :, k]) < 2e-5
+        L = L + (g[:5, :, k] * got).sum()
+    L.backward()
+    pairs = [(nn.layer1.x.grad, "d_xc"), (nn.layer1.y.grad, "d_yc"), (nn.layer1.h.grad.reshape(-1), "d_h"),
+             (nn.layer2.weight.grad, "d_W"), (nn.layer2.bias.grad, "d_b")]
+    for got, key in pairs:
+        e_new = mixed_err(got.cpu().numpy(), c[key + "_f64"])
+        e_ref = mixed_err(c[key + "_f32"], c[key + "_f64"])
+        assert e_new < 2e-5 and e_new < 3 * e_ref + 5e-6, (name, key, e_new, e_ref)
+
+
+def test_plot_grid_forward_is_u_only_and_matches(on_gpu):
+    from spinn_b200 import spinn2d
+    from spinn_b200.common import tensor
+    c = load_case("g2d_k1")
+    nn = spinn2d.SPINN2D(_StubPDE((c["xf"], c["yf"]), (c["xfix"], c["yfix"]), 1), spinn2d.gaussian).to("cuda")
+    with torch.no_grad():
+        nn.layer2.weight.copy_(tensor(c["W"]))
+        nn.layer1.h.copy_(tensor(c["h"]))
+    u = nn(tensor(c["x"]), tensor(c["y"]))             # no requires_grad -> level 0
+    assert u.shape == (len(c["x"]),) and not u.requires_grad or u.grad_fn is not None
+
+
+def _traj(name):
+    d = np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
+    return d["loss"], [str(a) for a in d["args"]], d["errors"]
+
+
+@pytest.mark.parametrize("name,modname", [
+    ("ode3", "ode3"), ("ode3_softplus", "ode3"),
+    ("poisson2d_sine", "poisson2d_sine"), ("poisson2d_sine_softplus", "poisson2d_sine"),
+    ("irreg", "poisson2d_irreg_dom"), ("cavity", "cavity")])
+def test_config_trajectory_on_gpu_matches_reference(name, modname):
+    import importlib
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    ref, args, ref_err = _traj(name)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    app = mod.make_app()
+    app.run(args=args + ["--gpu"])
+    loss = np.asarray(app.solver.loss)
+    n = min(len(loss), len(ref))
+    assert n == len(ref)
+    rel = np.abs(loss[:n] - ref[:n]) / np.abs(ref[:n])
+    assert rel[:10].max() < 5e-5, (name, rel[:10].max())
+    assert rel.max() < 3e-3, (name, rel.max())
+    err = app.plotter.get_error()
+    if ref_err[2] > 0:
+        assert abs(err[2] - ref_err[2]) < 0.01 * ref_err[2] + 1e-6, (name, err, ref_err)
