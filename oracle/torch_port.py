@@ -152,3 +152,109 @@ def poisson_interior_step(kind, x, y, xc, yc, h, W, b, n_total):
     loss = (res ** 2).sum() / n_total
     loss.backward()
     return float(loss.detach())
+
+
+# --------------------------------------------------------------------------- #
+# nn.Module form of the same dense algorithm (same parameter names as the
+# reference: layer1.x/.y/.h, layer2.weight/.bias; 1-D layer1.center), so that the
+# problem classes / Optimizer of spinn_b200 can drive the REFERENCE ALGORITHM on
+# any device.  Used by tests and by tools/train_step_bench.py as the "reference
+# eager path on the same GPU" (SURVEY.md section 6).  Follows code/spinn2d.py:97-188
+# and code/spinn1d.py:88-171.
+# --------------------------------------------------------------------------- #
+class _Shift2D(torch.nn.Module):
+    def __init__(self, points, fixed, device):
+        super().__init__()
+        t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), dtype=torch.float32, device=device)
+        px, fx = np.asarray(points[0], float), np.asarray(fixed[0], float)
+        self.n = n = px.size + fx.size
+        span = np.ptp(np.hstack((px, fx))) if fx.size else np.ptp(px)
+        self.x = torch.nn.Parameter(t(points[0]))
+        self.y = torch.nn.Parameter(t(points[1]))
+        self.xf, self.yf = t(fixed[0]), t(fixed[1])
+        self.h = torch.nn.Parameter((span / np.sqrt(n)) * torch.ones(n, device=device))
+
+    def centers(self):
+        return torch.cat((self.x, self.xf)), torch.cat((self.y, self.yf))
+
+
+class DenseSPINN2D(torch.nn.Module):
+    """Dense eager 2-D SPINN: materialises (N, M) tensors; autograd does the rest."""
+
+    @classmethod
+    def from_args(cls, pde, activation, args):
+        return cls(pde, activation)
+
+    @classmethod
+    def setup_argparse(cls, parser, **kw):
+        parser.add_argument("--fixed-h", dest="fixed_h", action="store_true", default=False)
+        parser.add_argument("--pu", dest="pu", action="store_true", default=False)
+
+    def __init__(self, pde, activation, device=None):
+        super().__init__()
+        from spinn_b200 import common
+        device = common.device() if device is None else device
+        self.kind = "gaussian" if getattr(activation, "__name__", "") == "gaussian" else "softplus"
+        self.layer1 = _Shift2D(pde.nodes(), pde.fixed_nodes(), device)
+        self.layer2 = torch.nn.Linear(self.layer1.n, pde.n_vars()).to(device)
+        self.layer2.weight.data.fill_(0.0)
+        self.layer2.bias.data.fill_(0.0)
+
+    def forward(self, x, y):
+        xc, yc = self.layer1.centers()
+        return forward2d(self.kind, x, y, xc, yc, self.layer1.h, self.layer2.weight, self.layer2.bias).squeeze()
+
+    def centers(self):
+        return self.layer1.centers()
+
+    def widths(self):
+        return self.layer1.h
+
+    def weights(self):
+        return self.layer2.weight
+
+
+class _Shift1D(torch.nn.Module):
+    def __init__(self, points, fixed, device):
+        super().__init__()
+        t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), dtype=torch.float32, device=device)
+        p, f = np.asarray(points, float).ravel(), np.asarray(fixed, float).ravel()
+        self.n = n = p.size + f.size
+        allx = np.hstack((p, f)) if f.size else p
+        self.center = torch.nn.Parameter(t(p))
+        self.fixed = t(f)
+        self.h = torch.nn.Parameter(((allx.max() - allx.min()) / n) * torch.ones(n, device=device))
+
+
+class DenseSPINN1D(torch.nn.Module):
+    @classmethod
+    def from_args(cls, pde, activation, args):
+        return cls(pde, activation)
+
+    @classmethod
+    def setup_argparse(cls, parser, **kw):
+        parser.add_argument("--fixed-h", dest="fixed_h", action="store_true", default=False)
+        parser.add_argument("--pu", dest="pu", action="store_true", default=False)
+
+    def __init__(self, pde, activation, device=None):
+        super().__init__()
+        from spinn_b200 import common
+        device = common.device() if device is None else device
+        self.kind = "gaussian" if getattr(activation, "__name__", "") == "gaussian" else "softplus"
+        self.layer1 = _Shift1D(pde.nodes(), pde.fixed_nodes(), device)
+        self.layer2 = torch.nn.Linear(self.layer1.n, pde.n_vars()).to(device)
+        self.layer2.weight.data.fill_(0.0)
+        self.layer2.bias.data.fill_(0.0)
+
+    def forward(self, x):
+        xc = torch.cat((self.layer1.center, self.layer1.fixed))
+        return forward1d(self.kind, x, xc, self.layer1.h, self.layer2.weight, self.layer2.bias).squeeze()
+
+    def centers(self):
+        return torch.cat((self.layer1.center, self.layer1.fixed))
+
+    def widths(self):
+        return self.layer1.h
+
+    def weights(self):
+        return self.layer2.weight

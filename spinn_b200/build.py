@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libspinn_b200.so")
-SOURCES = ["spinn_kernels.cu"]
+SOURCES = ["spinn_kernels.cu", "microbench.cu"]
 HEADERS = ["spinn_math.cuh", os.path.join("..", "..", "include", "spinn_b200.h")]
 
 NVCC_FLAGS = [

@@ -21,6 +21,8 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/spinn_b200.h"
 #include "spinn_math.cuh"
@@ -149,75 +151,182 @@ __global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict_
 }
 
 // -----------------------------------------------------------------------------
-// FAST forward: 2-D Gaussian, K=1.  Thread = P consecutive points (registers),
-// node-pair records broadcast from shared memory, packed f32x2 math where the two
-// lanes are the two nodes of a pair.
+// tuning knobs (production defaults; SPINN_TUNE="fwd=<id>,bwd=<id>,waves=<n>" overrides
+// them at call time -- used by tools/tune.py to pick the defaults on the box)
 // -----------------------------------------------------------------------------
-constexpr int FWD_THREADS = 256;
+struct FwdCfg { int p, threads, minb, unroll; };
+struct BwdCfg { int q, threads, minb, tile; };
+static const FwdCfg FWD_CFGS[] = {
+    {4, 256, 2, 2},   // 0
+    {2, 512, 2, 2},   // 1
+    {1, 512, 2, 4},   // 2
+    {2, 384, 2, 2},   // 3
+    {8, 128, 2, 1},   // 4
+    {4, 256, 2, 1},   // 5
+    {2, 256, 2, 4},   // 6
+    {4, 256, 2, 2},   // 7  all scalar
+    {4, 256, 2, 2},   // 8  packed geometry, scalar accumulation
+    {2, 512, 2, 2},   // 9  all scalar, more warps
+    {4, 256, 2, 2},   // 10 scalar geometry, packed accumulation
+};
+static const BwdCfg BWD_CFGS[] = {
+    {2, 128, 4, 256},  // 0
+    {1, 128, 8, 256},  // 1
+    {2, 256, 2, 256},  // 2
+    {4, 128, 2, 256},  // 3
+    {2, 128, 4, 512},  // 4
+    {1, 256, 4, 256},  // 5
+    {1, 128, 6, 512},  // 6
+    {2, 128, 4, 256},  // 7  all scalar
+    {2, 128, 4, 256},  // 8  packed math, scalar accumulation
+    {1, 128, 8, 256},  // 9  all scalar, more warps
+    {2, 128, 4, 256},  // 10 scalar math, packed accumulation
+};
+constexpr int N_FWD_CFGS = sizeof(FWD_CFGS) / sizeof(FWD_CFGS[0]);
+constexpr int N_BWD_CFGS = sizeof(BWD_CFGS) / sizeof(BWD_CFGS[0]);
+constexpr int FWD_DEFAULT = 6, BWD_DEFAULT = 2, WAVES_DEFAULT = 2;   // picked with tools/tune.py on B200
 
-template <int P, bool MIXED>
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+struct Tune { int fwd, bwd, waves; };
+static Tune get_tune() {
+  Tune t = {FWD_DEFAULT, BWD_DEFAULT, WAVES_DEFAULT};
+  const char* e = getenv("SPINN_TUNE");
+  if (e) {
+    const char* q;
+    if ((q = strstr(e, "fwd="))) t.fwd = atoi(q + 4);
+    if ((q = strstr(e, "bwd="))) t.bwd = atoi(q + 4);
+    if ((q = strstr(e, "waves="))) t.waves = atoi(q + 6);
+  }
+  if (t.fwd < 0 || t.fwd >= N_FWD_CFGS) t.fwd = FWD_DEFAULT;
+  if (t.bwd < 0 || t.bwd >= N_BWD_CFGS) t.bwd = BWD_DEFAULT;
+  if (t.waves < 1 || t.waves > 64) t.waves = WAVES_DEFAULT;
+  return t;
+}
+
+// -----------------------------------------------------------------------------
+// FAST forward: 2-D Gaussian, K=1.  Persistent CTAs; the node-pair records (the whole
+// node set when it fits: 48 B per pair, 96 KB at M=4096) are staged in shared memory
+// ONCE per CTA; each WARP then walks warp-tiles of 32*P consecutive points (thread =
+// P consecutive points in registers, coalesced vector loads/stores).  Packed f32x2
+// math where the two lanes are the two nodes of a pair; records are broadcast LDS.128.
+// -----------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void load_points(const float* __restrict__ p, long long i0, int N, bool vec,
+                                            float* out) {
+  if (vec && i0 + P - 1 < N) {
+    if (P % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < P / 4; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i0 + 4 * k);
+        out[(4 * k) % P] = v.x; out[(4 * k + 1) % P] = v.y; out[(4 * k + 2) % P] = v.z; out[(4 * k + 3) % P] = v.w;
+      }
+      return;
+    }
+    if (P == 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p + i0);
+      out[0] = v.x; out[1 % P] = v.y;
+      return;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q) out[q] = (i0 + q < N) ? p[i0 + q] : 0.f;
+}
+
+template <int P>
+__device__ __forceinline__ void store_points(float* __restrict__ p, long long i0, int N, bool vec,
+                                             const float* v) {
+  if (vec && i0 + P - 1 < N) {
+    if (P % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < P / 4; ++k)
+        *reinterpret_cast<float4*>(p + i0 + 4 * k) =
+            make_float4(v[(4 * k) % P], v[(4 * k + 1) % P], v[(4 * k + 2) % P], v[(4 * k + 3) % P]);
+      return;
+    }
+    if (P == 2) {
+      *reinterpret_cast<float2*>(p + i0) = make_float2(v[0], v[1 % P]);
+      return;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+    if (i0 + q < N) p[i0 + q] = v[q];
+}
+
+template <int P, bool MIXED, int UNROLL, int PK, int PA>
+__device__ __forceinline__ void g2k1_fwd_inner(const float4* __restrict__ sm4, int n,
+                                               const float2* x2, const float2* y2,
+                                               float2 (*acc)[MIXED ? 6 : 5]) {
+#pragma unroll UNROLL
+  for (int p = 0; p < n; ++p) {
+    const float4 A = sm4[3 * p + 0], B = sm4[3 * p + 1], C = sm4[3 * p + 2];
+    const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
+    const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
+#pragma unroll
+    for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED, PK, PA>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+  }
+}
+
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, int PK, int PA>
+__global__ void __launch_bounds__(THREADS, MINB)
 g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
                 const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
   constexpr int NJ = MIXED ? 6 : 5;
+  constexpr int WPC = THREADS / 32;
   extern __shared__ float4 sm4[];
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * P;
+  const int lane = threadIdx.x & 31;
+  // slot-major warp rank: warps 0-3 of every CTA first, then warps 4-7, ... so that the LAST
+  // (partial) wave of warp-tiles is spread over all SMs / sub-partitions instead of leaving
+  // whole CTAs idle
+  const int lw = threadIdx.x >> 5;
+  const long long gw = (long long)(lw >> 2) * ((long long)gridDim.x * 4) + (long long)blockIdx.x * 4 + (lw & 3);
+  const long long nwarps = (long long)gridDim.x * WPC;
+  const long long nwt = ((long long)N + 32 * P - 1) / (32 * P);
+  const long long iters = (nwt + nwarps - 1) / nwarps;
+  const bool single = npairs <= tile_pairs;
+  const bool vec = vec_ok != 0;
+  const float b0 = bias ? bias[0] : 0.f;
 
-  float px[P], py[P];
-  if (P == 4 && vec_ok && i0 + 3 < N) {
-    float4 a = *reinterpret_cast<const float4*>(x + i0);
-    float4 b = *reinterpret_cast<const float4*>(y + i0);
-    px[0] = a.x; px[1 % P] = a.y; px[2 % P] = a.z; px[3 % P] = a.w;
-    py[0] = b.x; py[1 % P] = b.y; py[2 % P] = b.z; py[3 % P] = b.w;
-  } else {
+  if (single) {
+    for (int e = threadIdx.x; e < 3 * npairs; e += THREADS) sm4[e] = recs[e];
+    __syncthreads();
+  }
+  for (long long it = 0; it < iters; ++it) {
+    const long long wt = gw + it * nwarps;
+    const bool active = wt < nwt;                  // warp-uniform
+    if (single && !active) break;                  // no further block-level syncs on this path
+    const long long i0 = (wt * 32 + lane) * P;
+    float px[P], py[P];
+    load_points<P>(x, active ? i0 : (long long)N, N, vec, px);
+    load_points<P>(y, active ? i0 : (long long)N, N, vec, py);
+    float2 x2[P], y2[P], acc[P][NJ];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-      px[q] = (i0 + q < N) ? x[i0 + q] : 0.f;
-      py[q] = (i0 + q < N) ? y[i0 + q] : 0.f;
+      x2[q] = f2dup(px[q]);
+      y2[q] = f2dup(py[q]);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
     }
-  }
-  float2 x2[P], y2[P], acc[P][NJ];
-#pragma unroll
-  for (int q = 0; q < P; ++q) {
-    x2[q] = f2dup(px[q]);
-    y2[q] = f2dup(py[q]);
-#pragma unroll
-    for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
-  }
-
-  for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
-    const int n = min(tile_pairs, npairs - t0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) sm4[e] = recs[3 * (size_t)t0 + e];
-    __syncthreads();
-#pragma unroll 2
-    for (int p = 0; p < n; ++p) {
-      const float4 A = sm4[3 * p + 0], B = sm4[3 * p + 1], C = sm4[3 * p + 2];
-      const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
-      const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
-#pragma unroll
-      for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+    if (single) {
+      g2k1_fwd_inner<P, MIXED, UNROLL, PK, PA>(sm4, npairs, x2, y2, acc);
+    } else {
+      for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
+        const int n = min(tile_pairs, npairs - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 3 * n; e += THREADS) sm4[e] = recs[3 * (size_t)t0 + e];
+        __syncthreads();
+        g2k1_fwd_inner<P, MIXED, UNROLL, PK, PA>(sm4, n, x2, y2, acc);
+      }
     }
-  }
-
-  const float b0 = bias ? bias[0] : 0.f;
-  float out[NJ][P];
+    if (active) {
 #pragma unroll
-  for (int q = 0; q < P; ++q)
+      for (int a = 0; a < NJ; ++a) {
+        float out[P];
 #pragma unroll
-    for (int a = 0; a < NJ; ++a) out[a][q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
-  if (P == 4 && vec_ok && i0 + 3 < N) {
-#pragma unroll
-    for (int a = 0; a < NJ; ++a)
-      *reinterpret_cast<float4*>(jets + (size_t)a * N + i0) =
-          make_float4(out[a][0], out[a][1 % P], out[a][2 % P], out[a][3 % P]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < P; ++q)
-      if (i0 + q < N)
-#pragma unroll
-        for (int a = 0; a < NJ; ++a) jets[(size_t)a * N + i0 + q] = out[a][q];
+        for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
+        store_points<P>(jets + (size_t)a * N, i0, N, vec, out);
+      }
+    }
   }
 }
 
@@ -229,20 +338,17 @@ g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
 // Two-level accumulation (per tile, then per chunk) keeps fp32 round-off at the
 // level of the reference's pairwise torch.sum.
 // -----------------------------------------------------------------------------
-constexpr int BWD_THREADS = 128;
-constexpr int BWD_TILE_PAIRS = 256;    // point pairs per smem tile (16 KB)
-
-template <int Q>
-__global__ void __launch_bounds__(BWD_THREADS, 4)
+template <int Q, int THREADS, int MINB, int TILE, int PK, int PA>
+__global__ void __launch_bounds__(THREADS, MINB)
 g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
                 const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
-  __shared__ float4 sm4[4 * BWD_TILE_PAIRS];
-  const int jbase = blockIdx.x * (Q * BWD_THREADS) + threadIdx.x;
+  __shared__ float4 sm4[4 * TILE];
+  const int jbase = blockIdx.x * (Q * THREADS) + threadIdx.x;
   float2 nc[Q], nd[Q], rp[Q], nrt[Q], rho[Q], nk1[Q], k2p[Q];
   float hq[Q], wq[Q];
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
-    const int j = jbase + q * BWD_THREADS;
+    const int j = jbase + q * THREADS;
     const float c = soa[j], d = soa[(size_t)Mp + j];
     hq[q] = soa[2 * (size_t)Mp + j];
     wq[q] = soa[4 * (size_t)Mp + j];
@@ -258,10 +364,10 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
 
   const int p_begin = blockIdx.y * pairs_per_chunk;
   const int p_end = min(N2, p_begin + pairs_per_chunk);
-  for (int t0 = p_begin; t0 < p_end; t0 += BWD_TILE_PAIRS) {
-    const int n = min(BWD_TILE_PAIRS, p_end - t0);
+  for (int t0 = p_begin; t0 < p_end; t0 += TILE) {
+    const int n = min(TILE, p_end - t0);
     __syncthreads();
-    for (int e = threadIdx.x; e < 4 * n; e += BWD_THREADS) sm4[e] = ptrecs[4 * (size_t)t0 + e];
+    for (int e = threadIdx.x; e < 4 * n; e += THREADS) sm4[e] = ptrecs[4 * (size_t)t0 + e];
     __syncthreads();
     float2 acc[Q][4];
 #pragma unroll
@@ -276,7 +382,7 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
       const float2 g4 = f2(D.x, D.y);
 #pragma unroll
       for (int q = 0; q < Q; ++q)
-        g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q],
+        g2_bwd_pair<PK, PA>(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q],
                     acc[q]);
     }
 #pragma unroll
@@ -288,7 +394,7 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
   float* out = partials + (size_t)blockIdx.y * 4 * Mp;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
-    const int j = jbase + q * BWD_THREADS;
+    const int j = jbase + q * THREADS;
     float dW, dc, dd, dh;
     g2_bwd_finish(hq[q], wq[q], tot[q][0], tot[q][1], tot[q][2], tot[q][3], &dW, &dc, &dd, &dh);
     out[j] = dc;
@@ -411,7 +517,7 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
 // -----------------------------------------------------------------------------
 // second stage: bias gradient partials, chunk reduction, scalar-h reduction
 // -----------------------------------------------------------------------------
-constexpr int BIAS_BLOCKS = 64;
+constexpr int BIAS_BLOCKS = 1024;
 
 __global__ void __launch_bounds__(256)
 bias_partial_kernel(int N, int K, const float* __restrict__ g0, float* __restrict__ bpart) {
@@ -435,28 +541,52 @@ bias_partial_kernel(int N, int K, const float* __restrict__ g0, float* __restric
   }
 }
 
-__global__ void __launch_bounds__(128)
+// grid (ceil(M/32), nacc + 1), block (32, 8): thread (tx, ty) sums chunks ty, ty+8, ... of one
+// (row, node) in fp64, the 8 partial sums are combined in a fixed order (deterministic); the
+// extra grid row reduces the bias partials.
+__global__ void __launch_bounds__(256)
 finalize_kernel(int dim, int K, int M, int Mfree, int Mp, int C, const float* __restrict__ partials,
                 const float* __restrict__ bpart, int nb, float* __restrict__ d_xc,
                 float* __restrict__ d_yc, float* __restrict__ d_h, float* __restrict__ d_W,
                 float* __restrict__ d_bias) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[8][33];
   const int nacc = dim + 1 + K;
-  if (j < M) {
-    for (int a = 0; a < nacc; ++a) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int a = blockIdx.y;
+  if (a == nacc) {                       // bias row
+    if (blockIdx.x != 0 || d_bias == nullptr) return;
+    const int t = ty * 32 + tx;
+    for (int k = 0; k < K; ++k) {
       double s = 0.0;
-      for (int c = 0; c < C; ++c) s += (double)partials[((size_t)c * nacc + a) * Mp + j];
-      const float v = (float)s;
-      if (a == 0) { if (j < Mfree) d_xc[j] = v; }
-      else if (dim == 2 && a == 1) { if (j < Mfree) d_yc[j] = v; }
-      else if (a == dim) d_h[j] = v;
-      else d_W[(size_t)(a - dim - 1) * M + j] = v;
+      for (int b = t; b < nb; b += 256) s += (double)bpart[b * K + k];
+      __syncthreads();
+      red[ty][tx] = s;
+      __syncthreads();
+      if (ty == 0) {
+        double v = 0.0;
+        for (int r = 0; r < 8; ++r) v += red[r][tx];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tx == 0) d_bias[k] = (float)v;
+      }
     }
+    return;
   }
-  if (blockIdx.x == 0 && threadIdx.x < K && d_bias != nullptr) {
-    double s = 0.0;
-    for (int b = 0; b < nb; ++b) s += (double)bpart[b * K + threadIdx.x];
-    d_bias[threadIdx.x] = (float)s;
+  const int j = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (j < M)
+    for (int c = ty; c < C; c += 8) s += (double)partials[((size_t)c * nacc + a) * Mp + j];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < M) {
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += red[r][tx];
+    const float f = (float)v;
+    if (a == 0) { if (j < Mfree) d_xc[j] = f; }
+    else if (dim == 2 && a == 1) { if (j < Mfree) d_yc[j] = f; }
+    else if (a == dim) d_h[j] = f;
+    else d_W[(size_t)(a - dim - 1) * M + j] = f;
   }
 }
 
@@ -593,48 +723,70 @@ struct BwdPlan {
   int chunks;          // point chunks (grid.y)
   int per_chunk;       // points (generic) or point pairs (fast) per chunk
   int N2;              // fast: point pairs
+  int variant;         // fast: BWD_CFGS index
   size_t off_soa, off_pts, off_part, off_bias, off_htmp, ws_bytes;
 };
-
-constexpr int BWD_Q = 2;
 
 static bool bwd_is_fast(int dim, int kind, int level, int K) {
   return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && level == 2;
 }
 
+// chunking: enough (node group x point chunk) blocks for `waves` waves of resident CTAs
+static int chunks_for(int sms, int waves, int groups, long long units, int tile, int blocks_per_sm,
+                      int* per_chunk) {
+  long long target = (long long)sms * blocks_per_sm * waves;
+  int c = (int)((target + groups - 1) / groups);
+  if (c < 1) c = 1;
+  long long per = (units + c - 1) / c;
+  per = (per + tile - 1) / tile * tile;
+  if (per < tile) per = tile;
+  *per_chunk = (int)per;
+  c = (int)((units + per - 1) / per);
+  return c < 1 ? 1 : c;
+}
+
 static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool worst) {
   BwdPlan p;
   p.fast = bwd_is_fast(dim, kind, level, K);
+  const Tune tune = get_tune();
   const int sms = sm_count();
   const int nacc = dim + 1 + K;
-  // worst-case sizing uses the larger padding and the larger chunk count of the two paths
-  const int group_fast = BWD_Q * BWD_THREADS, group_gen = GEN_THREADS;
-  const int Mp_fast = round_up_i(M, group_fast), Mp_gen = round_up_i(M, group_gen);
   p.N2 = (N + 1) / 2;
-  auto chunks_for = [&](int groups, long long units, int tile, int blocks_per_sm, int* per_chunk) {
-    long long target = (long long)sms * blocks_per_sm * 2;      // ~2 waves of resident blocks
-    int c = (int)((target + groups - 1) / groups);
-    if (c < 1) c = 1;
-    long long per = (units + c - 1) / c;
-    per = (per + tile - 1) / tile * tile;
-    if (per < tile) per = tile;
-    *per_chunk = (int)per;
-    c = (int)((units + per - 1) / per);
-    return c < 1 ? 1 : c;
-  };
-  int pc_fast = 0, pc_gen = 0;
-  const int c_fast = chunks_for(Mp_fast / group_fast, p.N2, BWD_TILE_PAIRS, 4, &pc_fast);
-  const int c_gen = chunks_for(Mp_gen / group_gen, N, GEN_TILE_POINTS, 4, &pc_gen);
-  if (p.fast) { p.Mp = Mp_fast; p.node_groups = Mp_fast / group_fast; p.chunks = c_fast; p.per_chunk = pc_fast; }
-  else { p.Mp = Mp_gen; p.node_groups = Mp_gen / group_gen; p.chunks = c_gen; p.per_chunk = pc_gen; }
-  const int Mp_w = worst ? (Mp_fast > Mp_gen ? Mp_fast : Mp_gen) : p.Mp;
-  const int c_w = worst ? (c_fast > c_gen ? c_fast : c_gen) : p.chunks;
+  p.variant = tune.bwd;
+  // generic path
+  const int Mp_gen = round_up_i(M, GEN_THREADS);
+  int pc_gen = 0;
+  const int c_gen = chunks_for(sms, 2, Mp_gen / GEN_THREADS, N, GEN_TILE_POINTS, 4, &pc_gen);
+  // fast path (selected variant) + worst case over all variants / wave counts up to 8
+  const BwdCfg cfg = BWD_CFGS[tune.bwd];
+  const int group = cfg.q * cfg.threads;
+  const int Mp_fast = round_up_i(M, group);
+  int pc_fast = 0;
+  const int c_fast = chunks_for(sms, tune.waves, Mp_fast / group, p.N2, cfg.tile, cfg.minb, &pc_fast);
+  if (p.fast) { p.Mp = Mp_fast; p.node_groups = Mp_fast / group; p.chunks = c_fast; p.per_chunk = pc_fast; }
+  else { p.Mp = Mp_gen; p.node_groups = Mp_gen / GEN_THREADS; p.chunks = c_gen; p.per_chunk = pc_gen; }
+  size_t part_floats = (size_t)p.chunks * nacc * p.Mp;
+  size_t Mp_w = p.Mp;
+  if (worst) {
+    part_floats = (size_t)c_gen * nacc * Mp_gen;
+    Mp_w = Mp_gen;
+    for (int v = 0; v < N_BWD_CFGS; ++v) {
+      const BwdCfg c = BWD_CFGS[v];
+      const int g = c.q * c.threads, mp = round_up_i(M, g);
+      int pc = 0;
+      const int waves = tune.waves > 8 ? tune.waves : 8;
+      const int ch = chunks_for(sms, waves, mp / g, p.N2, c.tile, c.minb, &pc);
+      const size_t f = (size_t)ch * nacc * mp;
+      if (f > part_floats) part_floats = f;
+      if ((size_t)mp > Mp_w) Mp_w = mp;
+    }
+  }
   size_t off = 0;
   p.off_soa = off;  off += align_up((size_t)(dim + 2 + K) * Mp_w * sizeof(float), 256);
   p.off_pts = off;  off += (worst || p.fast) ? align_up((size_t)4 * p.N2 * sizeof(float4), 256) : 0;
-  p.off_part = off; off += align_up((size_t)c_w * nacc * Mp_w * sizeof(float), 256);
+  p.off_part = off; off += align_up(part_floats * sizeof(float), 256);
   p.off_bias = off; off += align_up((size_t)BIAS_BLOCKS * SPINN_MAX_K * sizeof(float), 256);
-  p.off_htmp = off; off += align_up((size_t)Mp_w * sizeof(float), 256);
+  p.off_htmp = off; off += align_up(Mp_w * sizeof(float), 256);
   p.ws_bytes = off;
   return p;
 }
@@ -739,17 +891,39 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const size_t smem = (size_t)3 * tile_pairs * sizeof(float4);
     const int vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)jets) % 16 == 0) && (N % 4 == 0);
     const bool mixed = level == 3;
-    const bool big = (long long)N >= (long long)4 * FWD_THREADS * sm_count();
-#define SPINN_LAUNCH_FAST_FWD(P_, MIX_)                                                        \
-  do {                                                                                         \
-    auto kfn = g2k1_fwd_kernel<P_, MIX_>;                                                      \
-    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));  \
-    const int threads = (P_ == 1 && N < 4096) ? 64 : FWD_THREADS;                              \
-    const int blocks = ceil_div_i(N, (long long)threads * P_);                                 \
-    kfn<<<blocks, threads, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok); \
+    const Tune tune = get_tune();
+    const int sms = sm_count();
+#define SPINN_LAUNCH_FAST_FWD(P_, T_, B_, U_, PK_, PA_)                                                     \
+  do {                                                                                              \
+    const long long nwt = ((long long)N + 32 * P_ - 1) / (32 * P_);                                 \
+    long long blocks = (nwt + (T_ / 32) - 1) / (T_ / 32);                                           \
+    if (blocks > (long long)sms * B_) blocks = (long long)sms * B_;                                 \
+    if (mixed) {                                                                                    \
+      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_, PK_, PA_>;                                           \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));     \
+      kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
+    } else {                                                                                        \
+      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_, PK_, PA_>;                                           \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));     \
+      kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
+    }                                                                                               \
   } while (0)
-    if (big) { if (mixed) SPINN_LAUNCH_FAST_FWD(4, true); else SPINN_LAUNCH_FAST_FWD(4, false); }
-    else     { if (mixed) SPINN_LAUNCH_FAST_FWD(1, true); else SPINN_LAUNCH_FAST_FWD(1, false); }
+    // small point sets: one point per thread so that every SM gets work
+    const bool small = (long long)N < (long long)32 * 4 * 8 * sms;
+    const int v = small ? 2 : tune.fwd;
+    switch (v) {
+      case 0: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 1, 1); break;
+      case 1: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2, 1, 1); break;
+      case 2: SPINN_LAUNCH_FAST_FWD(1, 512, 2, 4, 1, 1); break;
+      case 3: SPINN_LAUNCH_FAST_FWD(2, 384, 2, 2, 1, 1); break;
+      case 4: SPINN_LAUNCH_FAST_FWD(8, 128, 2, 1, 1, 1); break;
+      case 5: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 1, 1, 1); break;
+      case 6: SPINN_LAUNCH_FAST_FWD(2, 256, 2, 4, 1, 1); break;
+      case 7: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 0, 0); break;
+      case 8: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 1, 0); break;
+      case 9: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2, 0, 0); break;
+      default: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 0, 1); break;
+    }
 #undef SPINN_LAUNCH_FAST_FWD
     LAUNCH_CHECK("g2k1_fwd_kernel");
     return SPINN_OK;
@@ -816,7 +990,22 @@ static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     float4* ptrecs = (float4*)(base + p.off_pts);
     pack_points_g2bwd_kernel<<<ceil_div_i(p.N2, 256), 256, 0, s>>>(N, p.N2, x, y, gj, ptrecs);
     LAUNCH_CHECK("pack_points_g2bwd_kernel");
-    g2k1_bwd_kernel<BWD_Q><<<grid, BWD_THREADS, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);
+#define SPINN_LAUNCH_FAST_BWD(Q_, T_, B_, TILE_, PK_, PA_) \
+  g2k1_bwd_kernel<Q_, T_, B_, TILE_, PK_, PA_><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials)
+    switch (p.variant) {
+      case 0: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 1, 1); break;
+      case 1: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256, 1, 1); break;
+      case 2: SPINN_LAUNCH_FAST_BWD(2, 256, 2, 256, 1, 1); break;
+      case 3: SPINN_LAUNCH_FAST_BWD(4, 128, 2, 256, 1, 1); break;
+      case 4: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 512, 1, 1); break;
+      case 5: SPINN_LAUNCH_FAST_BWD(1, 256, 4, 256, 1, 1); break;
+      case 6: SPINN_LAUNCH_FAST_BWD(1, 128, 6, 512, 1, 1); break;
+      case 7: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 0, 0); break;
+      case 8: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 1, 0); break;
+      case 9: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256, 0, 0); break;
+      default: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 0, 1); break;
+    }
+#undef SPINN_LAUNCH_FAST_BWD
     LAUNCH_CHECK("g2k1_bwd_kernel");
   } else {
     if (dim == 2) {
@@ -834,7 +1023,7 @@ static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     bias_partial_kernel<<<nb, 256, 0, s>>>(N, K, gj, bpart);
     LAUNCH_CHECK("bias_partial_kernel");
   }
-  finalize_kernel<<<ceil_div_i(M, 128), 128, 0, s>>>(dim, K, M, M_free, p.Mp, p.chunks, partials, bpart,
+  finalize_kernel<<<dim3(ceil_div_i(M, 32), nacc + 1), dim3(32, 8), 0, s>>>(dim, K, M, M_free, p.Mp, p.chunks, partials, bpart,
                                                      nb, d_xc, d_yc, hs ? htmp : d_h, d_W, d_bias);
   LAUNCH_CHECK("finalize_kernel");
   if (hs) {

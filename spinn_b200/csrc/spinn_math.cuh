@@ -72,26 +72,27 @@ SP_HD float rcpf_fast(float x) {
 // ---- packed f32x2 helpers (FFMA2/FADD2/FMUL2 on sm_100a) --------------------
 SP_HD float2 f2(float a, float b) { return make_float2(a, b); }
 SP_HD float2 f2dup(float a) { return make_float2(a, a); }
+// MODE 1: packed FFMA2/FMUL2/FADD2;  MODE 0: two scalar instructions (same rounding).
+template <int MODE = 1>
 SP_HD float2 f2fma(float2 a, float2 b, float2 c) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-  return __ffma2_rn(a, b, c);
-#else
-  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+  if (MODE == 1) return __ffma2_rn(a, b, c);
 #endif
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
 }
+template <int MODE = 1>
 SP_HD float2 f2mul(float2 a, float2 b) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-  return __fmul2_rn(a, b);
-#else
-  return make_float2(a.x * b.x, a.y * b.y);
+  if (MODE == 1) return __fmul2_rn(a, b);
 #endif
+  return make_float2(a.x * b.x, a.y * b.y);
 }
+template <int MODE = 1>
 SP_HD float2 f2add(float2 a, float2 b) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-  return __fadd2_rn(a, b);
-#else
-  return make_float2(a.x + b.x, a.y + b.y);
+  if (MODE == 1) return __fadd2_rn(a, b);
 #endif
+  return make_float2(a.x + b.x, a.y + b.y);
 }
 SP_HD float2 f2ex2neg(float2 t) { return make_float2(ex2f_fast(-t.x), ex2f_fast(-t.y)); }
 
@@ -120,28 +121,30 @@ SP_HD G2FwdNode g2_fwd_node(float c, float d, float h, float W) {
 }
 
 // accumulators: u, ux, uy, uxx, uyy (, uxy); each lane = partial sum over one node parity
-template <bool MIXED>
+// PK: packing mode of the geometry / scaling instructions, PA: of the accumulating FMAs
+// (three distinct register-pair operands each; see tools/microbench.py for why this matters).
+template <bool MIXED, int PK = 1, int PA = 1>
 SP_HD void g2_fwd_pair(float2 x2, float2 y2, float2 nc, float2 nd, float2 rp,
                        float2 w0, float2 w1, float2 w2, float2* acc) {
   const float2 nsig2 = f2dup(-SIG2_F);
-  float2 X  = f2add(x2, nc);
-  float2 Y  = f2add(y2, nd);
-  float2 xi = f2mul(X, rp);
-  float2 et = f2mul(Y, rp);
-  float2 hx = f2fma(xi, xi, nsig2);
-  float2 hy = f2fma(et, et, nsig2);
-  float2 t  = f2add(hx, hy);
+  float2 X  = f2add<PK>(x2, nc);
+  float2 Y  = f2add<PK>(y2, nd);
+  float2 xi = f2mul<PK>(X, rp);
+  float2 et = f2mul<PK>(Y, rp);
+  float2 hx = f2fma<PK>(xi, xi, nsig2);
+  float2 hy = f2fma<PK>(et, et, nsig2);
+  float2 t  = f2add<PK>(hx, hy);
   float2 E  = f2ex2neg(t);
-  acc[0] = f2fma(w0, E, acc[0]);
-  float2 g = f2mul(w1, E);
-  acc[1] = f2fma(g, xi, acc[1]);
-  acc[2] = f2fma(g, et, acc[2]);
-  float2 e = f2mul(w2, E);
-  acc[3] = f2fma(e, hx, acc[3]);
-  acc[4] = f2fma(e, hy, acc[4]);
+  acc[0] = f2fma<PA>(w0, E, acc[0]);
+  float2 g = f2mul<PK>(w1, E);
+  acc[1] = f2fma<PA>(g, xi, acc[1]);
+  acc[2] = f2fma<PA>(g, et, acc[2]);
+  float2 e = f2mul<PK>(w2, E);
+  acc[3] = f2fma<PA>(e, hx, acc[3]);
+  acc[4] = f2fma<PA>(e, hy, acc[4]);
   if (MIXED) {
-    float2 xe = f2mul(xi, et);
-    acc[5] = f2fma(e, xe, acc[5]);
+    float2 xe = f2mul<PK>(xi, et);
+    acc[5] = f2fma<PA>(e, xe, acc[5]);
   }
 }
 
@@ -163,43 +166,44 @@ SP_HD G2BwdNode g2_bwd_node(float c, float d, float h) {
 }
 
 // acc[0]=A_W, acc[1]=-A_c, acc[2]=-A_d, acc[3]=-A_h  (backward algebra)
+template <int PK = 1, int PA = 1>
 SP_HD void g2_bwd_pair(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, float2 g3, float2 g4,
                        float2 nc, float2 nd, float2 rp, float2 nrt, float2 rho, float2 nk1,
                        float2 k2p, float2* acc) {
   const float2 nsig2 = f2dup(-SIG2_F);
-  float2 X  = f2add(x2, nc);
-  float2 Y  = f2add(y2, nd);
-  float2 xi = f2mul(X, rp);
-  float2 et = f2mul(Y, rp);
-  float2 hx = f2fma(xi, xi, nsig2);
-  float2 hy = f2fma(et, et, nsig2);
-  float2 t  = f2add(hx, hy);
+  float2 X  = f2add<PK>(x2, nc);
+  float2 Y  = f2add<PK>(y2, nd);
+  float2 xi = f2mul<PK>(X, rp);
+  float2 et = f2mul<PK>(Y, rp);
+  float2 hx = f2fma<PK>(xi, xi, nsig2);
+  float2 hy = f2fma<PK>(et, et, nsig2);
+  float2 t  = f2add<PK>(hx, hy);
   float2 E  = f2ex2neg(t);
-  float2 a  = f2mul(g1, xi);
-  float2 b  = f2mul(g2, et);
-  float2 q  = f2mul(g3, hx);
-  q = f2fma(g4, hy, q);
-  float2 bp = f2fma(rho, q, g0);
-  float2 ab = f2add(a, b);
-  float2 PE = f2fma(nrt, ab, bp);
-  float2 bx = f2fma(nrt, b, bp);
-  bx = f2fma(nk1, g3, bx);
-  float2 m  = f2mul(g1, hx);
-  float2 ncx = f2mul(xi, bx);
-  ncx = f2fma(nrt, m, ncx);
-  float2 by = f2fma(nrt, a, bp);
-  by = f2fma(nk1, g4, by);
-  float2 m2 = f2mul(g2, hy);
-  float2 ncy = f2mul(et, by);
-  ncy = f2fma(nrt, m2, ncy);
-  float2 nhh = f2mul(xi, ncx);
-  nhh = f2fma(et, ncy, nhh);
-  nhh = f2fma(nk1, q, nhh);
-  nhh = f2fma(k2p, ab, nhh);
-  acc[0] = f2fma(E, PE, acc[0]);
-  acc[1] = f2fma(E, ncx, acc[1]);
-  acc[2] = f2fma(E, ncy, acc[2]);
-  acc[3] = f2fma(E, nhh, acc[3]);
+  float2 a  = f2mul<PK>(g1, xi);
+  float2 b  = f2mul<PK>(g2, et);
+  float2 q  = f2mul<PK>(g3, hx);
+  q = f2fma<PK>(g4, hy, q);
+  float2 bp = f2fma<PK>(rho, q, g0);
+  float2 ab = f2add<PK>(a, b);
+  float2 PE = f2fma<PK>(nrt, ab, bp);
+  float2 bx = f2fma<PK>(nrt, b, bp);
+  bx = f2fma<PK>(nk1, g3, bx);
+  float2 m  = f2mul<PK>(g1, hx);
+  float2 ncx = f2mul<PK>(xi, bx);
+  ncx = f2fma<PK>(nrt, m, ncx);
+  float2 by = f2fma<PK>(nrt, a, bp);
+  by = f2fma<PK>(nk1, g4, by);
+  float2 m2 = f2mul<PK>(g2, hy);
+  float2 ncy = f2mul<PK>(et, by);
+  ncy = f2fma<PK>(nrt, m2, ncy);
+  float2 nhh = f2mul<PK>(xi, ncx);
+  nhh = f2fma<PK>(et, ncy, nhh);
+  nhh = f2fma<PK>(nk1, q, nhh);
+  nhh = f2fma<PK>(k2p, ab, nhh);
+  acc[0] = f2fma<PA>(E, PE, acc[0]);
+  acc[1] = f2fma<PA>(E, ncx, acc[1]);
+  acc[2] = f2fma<PA>(E, ncy, acc[2]);
+  acc[3] = f2fma<PA>(E, nhh, acc[3]);
 }
 
 // final per-node factors: dW = A_W/e, dc = W rt/e * (-A_c), dd likewise, dh = W rt/(e sigma) * (-A_h)

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Train-step time (ms per opt.step(closure)) of the four BASELINE configs on one GPU:
+the fused B200 path vs the reference's dense eager algorithm on the SAME GPU
+(oracle/torch_port.py:DenseSPINN*, driven by the same problem classes and Optimizer).
+
+    python tools/train_step_bench.py [--steps 200]
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import torch_port  # noqa: E402
+from spinn_b200 import common  # noqa: E402
+from spinn_b200.problems import cavity, ode3, poisson2d_irreg_dom, poisson2d_sine  # noqa: E402
+from spinn_b200.spinn1d import App1D, Plotter1D  # noqa: E402
+from spinn_b200.spinn2d import App2D, Plotter2D  # noqa: E402
+
+CONFIGS = {
+    "ode3": (ode3, ["--nodes", "3", "--samples", "60", "--lr", "1e-3", "--tol", "1e-30"]),
+    "poisson2d_sine": (poisson2d_sine, ["--nodes", "100", "--samples", "400", "--lr", "1e-3", "--tol", "1e-30"]),
+    "poisson2d_irreg_dom": (poisson2d_irreg_dom, ["--lr", "1e-3"]),
+    "cavity": (cavity, ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4"]),
+}
+
+
+def run(app, args, steps):
+    np.random.seed(0)
+    torch.manual_seed(0)
+    a = args + ["--gpu", "--n-train", str(steps), "--n-skip", str(10 ** 9)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        app.run(args=a)                      # includes warm-up effects; time a second solve below
+        torch.cuda.synchronize()
+        app.solver.n_train = steps
+        t0 = time.perf_counter()
+        app.solver.solve()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return 1e3 * dt / steps, app.solver.loss[-1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=200)
+    a = ap.parse_args()
+    out = {}
+    for name, (mod, args) in CONFIGS.items():
+        fused = mod.make_app()
+        ms_f, loss_f = run(fused, args, a.steps)
+        is1d = name == "ode3"
+        pde_cls, plot_cls = fused.pde_cls, fused.plotter_cls
+        dense_cls = torch_port.DenseSPINN1D if is1d else torch_port.DenseSPINN2D
+        dense = (App1D if is1d else App2D)(pde_cls=pde_cls, nn_cls=dense_cls, plotter_cls=plot_cls)
+        ms_d, loss_d = run(dense, args, a.steps)
+        out[name] = {"fused_ms_per_step": ms_f, "dense_eager_same_gpu_ms_per_step": ms_d,
+                     "speedup": ms_d / ms_f, "loss_fused": loss_f, "loss_dense": loss_d}
+        print(name, json.dumps(out[name]), flush=True)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Time the fast-kernel variants (SPINN_TUNE) on the BASELINE workload on this GPU.
+    python tools/tune.py [--samples N] [--fwd ids] [--bwd ids] [--waves list]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spinn_b200 import synthetic  # noqa: E402
+from spinn_b200.fused_step import PoissonInteriorStep  # noqa: E402
+
+
+def time_ms(fn, reps=4):
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=4194304)
+    ap.add_argument("--fwd", default="0,1,2,3,4,5,6")
+    ap.add_argument("--bwd", default="0,1,2,3,4,5,6")
+    ap.add_argument("--waves", default="2,4,8")
+    a = ap.parse_args()
+    pde, nn = synthetic.make_state(samples=a.samples, device="cuda")
+    xs, ys = (t.detach() for t in pde.p_samples)
+    N, M = xs.numel(), nn.layer1.n
+    os.environ["SPINN_TUNE"] = "fwd=0,bwd=0,waves=2"
+    step = PoissonInteriorStep(nn, xs, ys)
+    ref = step.run(all_reduce=False).clone()
+    ref_jets = step.jets.clone()
+    lib, P = step.lib, (lambda t: None if t is None else t.data_ptr())
+    l1, l2 = nn.layer1, nn.layer2
+    S = lambda: torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        assert lib.spinn2d_jets_fwd(0, 2, N, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y), P(l1.xf),
+                                    P(l1.yf), P(l1.h), 0, P(l2.weight), P(l2.bias), P(step.jets),
+                                    P(step.ws_f), step.ws_f.numel(), S()) == 0
+
+    def bwd():
+        p = step.pack
+        assert lib.spinn2d_jets_bwd(0, 2, N, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y), P(l1.xf),
+                                    P(l1.yf), P(l1.h), 0, P(l2.weight), P(step.gjets), P(p.view("d_x")),
+                                    P(p.view("d_y")), P(p.view("d_h")), P(p.view("d_W")), P(p.view("d_b")),
+                                    P(step.ws_b), step.ws_b.numel(), S()) == 0
+
+    print(f"N={N} M={M}")
+    for v in [int(t) for t in a.fwd.split(",") if t]:
+        os.environ["SPINN_TUNE"] = f"fwd={v},bwd=0,waves=2"
+        step.jets.zero_()
+        ms = time_ms(fwd)
+        err = float((step.jets - ref_jets).abs().max() / ref_jets.abs().max())
+        print(f"fwd variant {v}: {ms:8.3f} ms   {N * M * 23 / ms / 1e9:7.2f} TFLOP/s   maxdiff {err:.2e}", flush=True)
+    for v in [int(t) for t in a.bwd.split(",") if t]:
+        for w in [int(t) for t in a.waves.split(",") if t]:
+            os.environ["SPINN_TUNE"] = f"fwd=0,bwd={v},waves={w}"
+            step.pack.flat.zero_()
+            ms = time_ms(bwd)
+            n = step.pack.slices["loss"][0]
+            err = float((step.pack.flat[:n] - ref[:n]).abs().max() / ref[:n].abs().max())
+            print(f"bwd variant {v} waves {w}: {ms:8.3f} ms   {N * M * 53 / ms / 1e9:7.2f} TFLOP/s   maxdiff {err:.2e}",
+                  flush=True)
+
+
+if __name__ == "__main__":
+    main()
