@@ -38,6 +38,11 @@ MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
 
 
+def workload_name(kind, n_points, n_nodes):
+    return (f"synthetic scaled Poisson2D: {n_points} collocation points x {n_nodes} nodes, "
+            f"{kind} kernel, K=1, 5 jets (u,ux,uy,uxx,uyy)")
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -150,9 +155,9 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "synthetic scaled Poisson2D: 4194304 collocation points x 4096 nodes "
-                               "(bounded CPU sample per step)", "kind": args.kind,
-                   "points_per_step": r["points"], "nodes": r["nodes"]},
+        "config": {"workload": workload_name(args.kind, args.samples, r["nodes"]), "points": args.samples,
+                   "nodes": r["nodes"], "kind": args.kind,
+                   "sample": f"each step = {r['points']} of the {args.samples} points (bounded CPU sample)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,19 +170,23 @@ def run_reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------
 def microbench_peaks(lib, dev):
-    """FP32 FMA and MUFU.EX2 issue rates measured on this GPU right now (lane-ops/s)."""
+    """FP32 and MUFU.EX2 instruction rates measured on this GPU right now (lane-ops/s) with the
+    probes of spinn_b200/csrc/microbench.cu (register operands, 64 resident warps per SM)."""
     import ctypes
     sink = torch.zeros(4, device=dev)
+    src = (1.0 + 1e-3 * torch.rand(64, device=dev)).float()
     out = {}
     s = torch.cuda.current_stream().cuda_stream
-    for which, name in ((0, "ffma"), (1, "ffma2"), (2, "ex2"), (3, "fwd_mix")):
+    probes = ((1, "ffma_3reg"), (0, "ffma_shared"), (2, "ffma2_shared"), (3, "ffma2_3pair"),
+              (4, "ffma2_bcast"), (10, "ex2"))
+    for which, name in probes:
         ops = ctypes.c_double(0.0)
-        iters = 4096 if which != 2 else 1024
         best = None
         for rep in range(3):
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             e0.record()
-            rc = lib.spinn_microbench(which, iters, SMS * 8, 256, sink.data_ptr(), ctypes.byref(ops), s)
+            rc = lib.spinn_microbench(which, 2048, SMS * 8, 256, src.data_ptr(), sink.data_ptr(),
+                                      ctypes.byref(ops), s)
             e1.record()
             torch.cuda.synchronize()
             assert rc == 0
@@ -288,9 +297,30 @@ def run_ours(args):
         out_host = torch.empty(pack.flat.numel(), dtype=torch.float32).pin_memory()
         params = [l1.x, l1.y, l1.h, l2.weight, l2.bias]
 
+        # Host->device copies run on a side stream, one step ahead (what a data loader does);
+        # every step still uploads its own inputs and downloads its own result inside the
+        # timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        staged = {}
+
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                x = xh.to(dev, non_blocking=True)
+                y = yh.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            staged["next"] = (x, y, ev)
+
         def e2e_step():
-            x = xh.to(dev, non_blocking=True).requires_grad_(True)
-            y = yh.to(dev, non_blocking=True).requires_grad_(True)
+            if "next" not in staged:
+                upload()
+            x, y, ev = staged.pop("next")
+            torch.cuda.current_stream().wait_event(ev)
+            x.record_stream(torch.cuda.current_stream())
+            y.record_stream(torch.cuda.current_stream())
+            upload()                                                   # inputs of the following step
+            x.requires_grad_(True)
+            y.requires_grad_(True)
             for p_ in params:
                 p_.grad = None
             u = nn(x, y)                                               # public plug-in call
@@ -325,6 +355,31 @@ def run_ours(args):
                "loss": float(out_host[pack.slices["loss"][0]]),
                "api": "SPINN2D.forward -> RegularPDE._compute_derivatives -> pde() -> loss.backward()"}
 
+    # ---- one full optimisation step through the plug-in surface (1 GPU only): interior (all
+    # local points) + boundary loss + backward + Adam + the per-step loss.item() sync, exactly
+    # Optimizer.closure / opt.step of common.py ----
+    train_step = None
+    if ws == 1 and not args.no_e2e:
+        from spinn_b200.common import Optimizer
+        from spinn_b200.spinn2d import Plotter2D
+        prev_w = [p_.detach().clone() for p_ in params]
+        solver = Optimizer(pde, nn, Plotter2D(pde, nn), n_train=1, n_skip=10 ** 9, lr=1e-3, plot=False)
+        solver.opt = torch.optim.Adam(nn.parameters(), lr=1e-3)
+        for _ in range(2):
+            solver.opt.step(solver.closure)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nts = max(3, args.steps // 2)
+        for _ in range(nts):
+            solver.opt.step(solver.closure)
+        torch.cuda.synchronize()
+        train_step = {"ms": 1e3 * (time.perf_counter() - t0) / nts, "steps": nts,
+                      "what": "opt.step(closure): interior %d pts + boundary %d pts + backward + Adam + "
+                              "loss.item(), points resident on the GPU" % (N, pde.b_samples[0].numel())}
+        with torch.no_grad():
+            for p_, w_ in zip(params, prev_w):
+                p_.copy_(w_)
+
     if rank != 0:
         if ws > 1:
             dist.barrier()
@@ -333,7 +388,7 @@ def run_ours(args):
     peaks = microbench_peaks(lib, dev)
     clocks = clk.summary()
     nominal_fp32 = SMS * LANES * 2 * NOMINAL_MHZ * 1e6          # flop/s
-    measured_fp32 = 2.0 * max(peaks["ffma"], peaks["ffma2"])     # flop/s from lane-FMA/s
+    measured_fp32 = 2.0 * max(peaks["ffma_3reg"], peaks["ffma_shared"], peaks["ffma2_shared"])  # flop/s
     ach_bwd = pairs_loc * FLOP_BWD / (ms_bwd * 1e-3)
     ach_fwd = pairs_loc * FLOP_FWD / (ms_fwd * 1e-3)
     ach_step = N * M * FLOP_PER_PAIR / (ms_step * 1e-3) / ws
@@ -347,7 +402,7 @@ def run_ours(args):
         "bound": "fp32", "kernel": "g2k1_bwd_kernel<2>",
         "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
         "frac": ach_bwd / measured_fp32, "traffic": None,
-        "peak_source": "in-run FFMA/FFMA2 microbenchmark (spinn_microbench), lane-FMA/s x 2",
+        "peak_source": "best in-run FMA probe (spinn_microbench: FFMA/FFMA2 chains, register operands, 64 warps/SM), lane-FMA/s x 2",
         "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
         "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR},
         "kernels": {
@@ -378,14 +433,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic scaled Poisson2D: {N} collocation points x {M} nodes, "
-                               f"{args.kind} kernel, K=1, 5 jets (u,ux,uy,uxx,uyy), point-sharded over {ws} GPU(s)",
+        "config": {"workload": workload_name(args.kind, N, M), "parallelism": f"points sharded over {ws} GPU(s)",
                    "points": N, "nodes": M, "points_per_gpu": n_loc, "kind": args.kind,
                    "l2_policy": "inputs larger than L2: per step x,y 8 B + jets 20 B + gjets 20 B + packed "
                                 "point records 32 B per point (>300 MB at 4M points vs 126 MB L2)",
                    "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
                                  if ws > 1 else "none (1 GPU)"},
-        "loss": loss, "train_step_ms": ms_step,
+        "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
         "clocks": clocks, "e2e": e2e, "gpu_launches": PoissonInteriorStep.LAUNCHES * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

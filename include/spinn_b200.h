@@ -110,13 +110,17 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
                              size_t workspace_bytes, void* stream);
 size_t spinn2d_poisson_residual_workspace_bytes(int N);
 
-/* ---- instruction-throughput microbenchmarks used to measure the roofline
- * denominators on the box (FP32 FMA, packed FFMA2, MUFU.EX2).  Runs `iters`
- * dependent-chain iterations per thread on a full grid and returns the number of
- * lane-operations executed (as double) in *ops; timing is the caller's (CUDA
- * events on `stream`).  which: 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 FFMA2+EX2 mix (7:1). */
-int spinn_microbench(int which, int iters, int blocks, int threads, float* sink,
-                     double* ops, void* stream);
+/* ---- instruction-throughput probes used to measure the roofline denominators on the box
+ * (spinn_b200/csrc/microbench.cu).  Every thread runs 8 independent float2 accumulator chains
+ * for `iters` iterations with operands held in registers loaded from `in` (>= 64 floats), so
+ * nothing folds into immediates.  *lane_ops receives the number of per-lane operations issued;
+ * timing is the caller's (CUDA events on `stream`).  which:
+ *   0 FFMA a=a*m+d (shared regs)   1 FFMA a=b*c+a (3 distinct regs)   2 FFMA2 a=a*m+d
+ *   3 FFMA2 a=b*c+a (3 distinct register pairs)   4 FFMA2 with a scalar-broadcast operand
+ *   5 FMUL2+FADD2   6 FFMA with immediate   7 half FFMA2 / half FFMA   8 FADD   9 FMUL
+ *   10 MUFU.EX2   11 (reserved)   12 FFMA2 with pairwise-reused operands */
+int spinn_microbench(int which, int iters, int blocks, int threads, const float* in, float* sink,
+                     double* lane_ops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,9 +4,9 @@ Same public names, argument meaning and behaviour as /root/reference/code/common
 (``device`` :14-21, ``tensor`` :24-28, ``PDE`` :31-92, ``Plotter`` :94-151,
 ``Optimizer`` :154-314, ``App`` :317-379) so that problem scripts written against
 the reference drive the B200 path unchanged.  Written from the behaviour, not
-from the text: flags are declared in tables, the training loop is split into
-small methods, and two optional throughput switches are added (``sync_every``,
-default 1 = reference behaviour).
+from the text: flags are declared in tables and the training loop is split into
+small methods.  One flag is new: ``--graph`` replays the training step as a CUDA
+graph (spinn_b200/graphed.py); without it the loop is the reference's.
 """
 from __future__ import annotations
 
@@ -161,18 +161,23 @@ class Optimizer:
         (("--lr",), "lr", 1e-2, float, "Learning rate."),
         (("--optimizer",), "optimizer", "Adam", ("Adam", "LBFGS"), "Optimizer to use."),
         (("-d", "--directory"), "directory", None, str, "Output directory (output files are dumped here)."),
+        # not in the reference: capture one training step in a CUDA graph (spinn_b200/graphed.py)
+        (("--graph",), "graph", False, None, "Replay the training step as a CUDA graph (Adam, --gpu)."),
     )
 
     @classmethod
     def from_args(cls, pde, nn, plotter, args):
         opt_class = {"Adam": torch.optim.Adam, "LBFGS": torch.optim.LBFGS}[args.optimizer]
+        if getattr(args, "graph", False) and cls is Optimizer:
+            from .graphed import GraphedOptimizer
+            cls = GraphedOptimizer
         return cls(pde, nn, plotter, n_train=args.n_train, n_skip=args.n_skip, tol=args.tol,
                    lr=args.lr, plot=args.plot, out_dir=args.directory, opt_class=opt_class)
 
     @classmethod
     def setup_argparse(cls, parser, **kw):
         # --plot is a pure CLI switch in the reference (kw does not override it)
-        add_flags(parser, cls.FLAGS, {k: v for k, v in kw.items() if k != "plot"})
+        add_flags(parser, cls.FLAGS, {k: v for k, v in kw.items() if k not in ("plot", "graph")})
 
     def __init__(self, pde, nn, plotter, n_train, n_skip=100, tol=1e-6, lr=1e-2, plot=True,
                  out_dir=None, opt_class=torch.optim.Adam):

@@ -1,6 +1,7 @@
 // microbench.cu -- instruction-throughput probes used to establish the FP32 / MUFU
-// roofline denominators on the box (spinn_microbench2).  Not on the product path.
+// roofline denominators on the box (spinn_microbench).  Not on the product path.
 #include <cuda_runtime.h>
+#include "../../include/spinn_b200.h"
 #include "spinn_math.cuh"
 using namespace spinn;
 
@@ -72,7 +73,7 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
   if (s == 123.456f) sink[0] = s;
 }
 
-extern "C" int spinn_microbench2(int which, int iters, int blocks, int threads, const float* in,
+extern "C" int spinn_microbench(int which, int iters, int blocks, int threads, const float* in,
                                  float* sink, double* lane_ops, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const double lanes = (double)blocks * threads * iters;

@@ -649,43 +649,6 @@ add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ o
 }
 
 // -----------------------------------------------------------------------------
-// microbenchmarks (roofline denominators measured on the box)
-// -----------------------------------------------------------------------------
-template <int WHICH>
-__global__ void __launch_bounds__(256)
-microbench_kernel(int iters, float* sink) {
-  const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
-  float2 a[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = f2(seed + k, seed - k);
-  const float2 m = f2(0.999999f, 1.000001f), c = f2(1e-9f, -1e-9f);
-  for (int it = 0; it < iters; ++it) {
-    if (WHICH == 0) {          // scalar FFMA, 16 independent chains
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k].x = fmaf(a[k].x, m.x, c.x); a[k].y = fmaf(a[k].y, m.y, c.y); }
-    } else if (WHICH == 1) {   // packed FFMA2, 8 independent chains
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = f2fma(a[k], m, c);
-    } else if (WHICH == 2) {   // MUFU.EX2, 16 independent chains
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k].x = ex2f_fast(a[k].x); a[k].y = ex2f_fast(a[k].y); }
-    } else {                   // the forward kernel's mix: 14 packed ops + 2 ex2 per group
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        float2 t = a[k];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) { t = f2fma(t, m, c); a[k + 1] = f2fma(a[k + 1], m, t); }
-        a[k] = f2(ex2f_fast(-fabsf(t.x)), ex2f_fast(-fabsf(t.y)));
-      }
-    }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y;
-  if (s == 123.456f) sink[0] = s;
-}
-
-// -----------------------------------------------------------------------------
 // planning
 // -----------------------------------------------------------------------------
 struct FwdPlan {
@@ -899,12 +862,20 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     long long blocks = (nwt + (T_ / 32) - 1) / (T_ / 32);                                           \
     if (blocks > (long long)sms * B_) blocks = (long long)sms * B_;                                 \
     if (mixed) {                                                                                    \
-      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_, PK_, PA_>;                                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));     \
+      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_, PK_, PA_>;                                   \
+      static bool configured = false; /* once per instantiation: not during graph capture */       \
+      if (!configured) {                                                                            \
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
+        configured = true;                                                                          \
+      }                                                                                             \
       kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
     } else {                                                                                        \
-      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_, PK_, PA_>;                                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));     \
+      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_, PK_, PA_>;                                  \
+      static bool configured = false;                                                               \
+      if (!configured) {                                                                            \
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
+        configured = true;                                                                          \
+      }                                                                                             \
       kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
     }                                                                                               \
   } while (0)
@@ -1118,22 +1089,6 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
   LAUNCH_CHECK("poisson_residual_kernel");
   add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
   LAUNCH_CHECK("add_partials_kernel");
-  return SPINN_OK;
-}
-
-int spinn_microbench(int which, int iters, int blocks, int threads, float* sink, double* ops,
-                     void* stream) {
-  if (which < 0 || which > 3 || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256 || !sink)
-    return fail(SPINN_E_BADARG, "bad microbench arguments");
-  cudaStream_t s = (cudaStream_t)stream;
-  const double lanes = (double)blocks * threads * iters;
-  switch (which) {
-    case 0: microbench_kernel<0><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
-    case 1: microbench_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
-    case 2: microbench_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 16; break;
-    default: microbench_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); if (ops) *ops = lanes * 4 * 28; break;
-  }
-  LAUNCH_CHECK("microbench_kernel");
   return SPINN_OK;
 }
 

@@ -1,0 +1,92 @@
+"""CUDA-graphed training step ("fused train step & sync removal").
+
+The small BASELINE configurations (ode3, poisson2d_sine, irregular domain, cavity) are
+launch- and sync-bound, not math-bound: one `opt.step(closure)` is ~100 tiny kernels plus a
+`loss.item()` round trip (reference common.py:242-248).  `GraphedOptimizer` runs the same
+loop as `common.Optimizer` but captures ONE step -- loss, backward (incl. the fused SPINN
+backward kernels, enqueued through the C ABI on the capturing stream) and the Adam update
+(`capturable=True`) -- into a CUDA graph and replays it; per-step losses go to a device
+buffer and are read back only when the loop reports (every `n_skip`).
+
+Requirements on the problem class (met by spinn_b200.problems.*): no host round trip inside
+`loss()` (boundary targets are cached on the device) and random sub-sampling through a static
+index buffer (`enable_static_sampling` / `graph_pre_step`).  Select with `--graph`.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from .common import Optimizer
+
+
+class GraphedOptimizer(Optimizer):
+    WARMUP_STEPS = 3          # eager steps before capture (they are real training steps)
+
+    def _body(self):
+        loss = self.pde.loss(self.nn)
+        loss.backward(retain_graph=True)
+        return loss
+
+    def _pre_step(self):
+        hook = getattr(self.pde, "graph_pre_step", None)
+        if hook is not None:
+            hook()
+
+    def solve(self):
+        if self.opt_class is not torch.optim.Adam:
+            raise NotImplementedError("--graph supports the Adam optimizer only")
+        params = list(self.nn.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("--graph needs --gpu")
+        if self.opt is None:
+            self.opt = torch.optim.Adam(params, lr=self.lr, capturable=True)
+        if hasattr(self.pde, "enable_static_sampling"):
+            self.pde.enable_static_sampling()
+        n_train = self.n_train
+        loss_buf = torch.zeros(max(n_train, 1), dtype=torch.float32, device=dev)
+        done_before = len(self.loss)
+        t0 = time.perf_counter()
+
+        # ---- eager warm-up on a side stream (PyTorch's capture recipe) ----
+        n_eager = min(self.WARMUP_STEPS, n_train)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(n_eager):
+                self._pre_step()
+                self.opt.zero_grad(set_to_none=True)
+                loss = self._body()
+                self.opt.step()
+                loss_buf[i].copy_(loss.detach())
+        torch.cuda.current_stream().wait_stream(side)
+
+        graph, static_loss = None, None
+        if n_train > n_eager:
+            self.opt.zero_grad(set_to_none=True)
+            self._pre_step_capture = True
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = self._body()
+                self.opt.step()
+
+        err, stop, i = 1.0, False, 0
+        for i in range(1, n_train + 1):
+            if i > n_eager:
+                self._pre_step()
+                graph.replay()
+                loss_buf[i - 1].copy_(static_loss.detach())
+            if err < self.tol:
+                stop = True
+            if i % self.n_skip == 0 or i == n_train or stop:
+                self.loss = self.loss[:done_before] + loss_buf[:i].tolist()      # one sync per report
+                err = self._report(i, loss_buf[i - 1])
+            if stop:
+                break
+        self.loss = self.loss[:done_before] + loss_buf[:i].tolist()
+        self.time_taken = time.perf_counter() - t0
+        print(f"Done. Took {self.time_taken:.3f} seconds.")
+        if self.plot:
+            self.plotter.show()

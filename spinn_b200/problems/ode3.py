@@ -26,7 +26,10 @@ class ODESimple(BasicODE):
         return x * (np.exp(-((x - (1.0 / 3.0)) ** 2) / K) - np.exp(-4.0 / (9.0 * K)))
 
     def boundary_loss(self, nn):
-        bc = nn(self.boundary()) - tensor(self.exact(self.xbn))
+        ub = getattr(self, "_ub", None)        # constant target, built once (reference: every step)
+        if ub is None or ub.device != self.xb.device:
+            ub = self._ub = tensor(self.exact(self.xbn))
+        bc = nn(self.boundary()) - ub
         return 10 * (bc ** 2).sum()
 
     def plot_points(self):

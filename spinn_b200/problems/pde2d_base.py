@@ -74,9 +74,30 @@ class RegularPDE(PDE):
     def interior(self):
         if abs(self.sample_frac - 1.0) < 1e-3:
             return self.p_samples
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
         x, y = self.p_samples
+        if getattr(self, "_idx_dev", None) is not None:      # CUDA-graph mode: static index buffer
+            return x[self._idx_dev], y[self._idx_dev]
+        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
         return x[idx], y[idx]
+
+    # -- CUDA-graph support (spinn_b200/graphed.py); not in the reference ------------------
+    def enable_static_sampling(self):
+        """Route the random sub-sample through a fixed device buffer that is refilled from the
+        SAME np.random.choice stream before every step (graph_pre_step)."""
+        if abs(self.sample_frac - 1.0) < 1e-3 or getattr(self, "_idx_dev", None) is not None:
+            return
+        import torch
+        dev = self.p_samples[0].device
+        self._idx_host = torch.empty(self.sample_size, dtype=torch.int64).pin_memory()
+        self._idx_dev = torch.zeros(self.sample_size, dtype=torch.int64, device=dev)
+
+    def graph_pre_step(self):
+        if getattr(self, "_idx_dev", None) is None:
+            return
+        import torch
+        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
+        self._idx_host.copy_(torch.from_numpy(idx))
+        self._idx_dev.copy_(self._idx_host, non_blocking=True)
 
     def boundary(self):
         return self.b_samples

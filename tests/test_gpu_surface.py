@@ -109,3 +109,28 @@ def test_config_trajectory_on_gpu_matches_reference(name, modname):
     err = app.plotter.get_error()
     if ref_err[2] > 0:
         assert abs(err[2] - ref_err[2]) < 0.01 * ref_err[2] + 1e-6, (name, err, ref_err)
+
+
+@pytest.mark.parametrize("name,modname,steps", [
+    ("ode3", "ode3", 120), ("poisson2d_sine", "poisson2d_sine", 80),
+    ("irreg", "poisson2d_irreg_dom", 40), ("cavity", "cavity", 60)])
+def test_cuda_graphed_step_follows_the_eager_trajectory(name, modname, steps):
+    """--graph (one training step captured in a CUDA graph and replayed) must reproduce the
+    reference's recorded loss history like the eager loop does, including the cavity's
+    per-step random sub-sampling (same np.random stream)."""
+    import importlib
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    ref, args, _ = _traj(name)
+    i = args.index("--n-train")
+    args[i + 1] = str(steps)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    app = mod.make_app()
+    app.run(args=args + ["--gpu", "--graph"])
+    from spinn_b200.graphed import GraphedOptimizer
+    assert isinstance(app.solver, GraphedOptimizer)
+    loss = np.asarray(app.solver.loss)
+    assert len(loss) == steps
+    rel = np.abs(loss - ref[:steps]) / np.abs(ref[:steps])
+    assert rel[:10].max() < 5e-5, (name, rel[:10].max())
+    assert rel.max() < 3e-3, (name, rel.max())

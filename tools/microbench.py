@@ -13,14 +13,11 @@ from spinn_b200 import _cabi  # noqa: E402
 NAMES = ["FFMA a=a*m+d (shared regs)", "FFMA a=b*c+a (3 distinct regs)", "FFMA2 a=a*m+d (shared)",
          "FFMA2 a=b*c+a (3 distinct pairs)", "FFMA2 a=b*bcast+a", "FMUL2+FADD2", "FFMA a=a*m+imm",
          "half FFMA2 + half FFMA (distinct)", "FADD distinct", "FMUL distinct", "MUFU.EX2",
-         "FFMA2 distinct + 1 EX2 per 8", "FFMA2 operands reused pairwise"]
+         "(reserved)", "FFMA2 operands reused pairwise"]
 
 
 def main():
-    lib = ctypes.CDLL(_cabi.LIB_PATH)
-    lib.spinn_microbench2.restype = ctypes.c_int
-    lib.spinn_microbench2.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p,
-                                                           ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]
+    lib = _cabi.load()
     dev = torch.device("cuda", 0)
     src = (1.0 + 1e-3 * torch.rand(64, device=dev)).float()
     sink = torch.zeros(4, device=dev)
@@ -34,7 +31,7 @@ def main():
             for _ in range(3):
                 a, b = torch.cuda.Event(True), torch.cuda.Event(True)
                 a.record()
-                rc = lib.spinn_microbench2(which, 2048, sms * occ_blocks, 256, src.data_ptr(), sink.data_ptr(),
+                rc = lib.spinn_microbench(which, 2048, sms * occ_blocks, 256, src.data_ptr(), sink.data_ptr(),
                                            ctypes.byref(ops), torch.cuda.current_stream().cuda_stream)
                 b.record()
                 torch.cuda.synchronize()

@@ -31,10 +31,10 @@ CONFIGS = {
 }
 
 
-def run(app, args, steps):
+def run(app, args, steps, extra=()):
     np.random.seed(0)
     torch.manual_seed(0)
-    a = args + ["--gpu", "--n-train", str(steps), "--n-skip", str(10 ** 9)]
+    a = args + ["--gpu", "--n-train", str(steps), "--n-skip", str(10 ** 9)] + list(extra)
     with contextlib.redirect_stdout(io.StringIO()):
         app.run(args=a)                      # includes warm-up effects; time a second solve below
         torch.cuda.synchronize()
@@ -54,13 +54,16 @@ def main():
     for name, (mod, args) in CONFIGS.items():
         fused = mod.make_app()
         ms_f, loss_f = run(fused, args, a.steps)
+        ms_g, loss_g = run(mod.make_app(), args, a.steps, extra=["--graph"])
         is1d = name == "ode3"
         pde_cls, plot_cls = fused.pde_cls, fused.plotter_cls
         dense_cls = torch_port.DenseSPINN1D if is1d else torch_port.DenseSPINN2D
         dense = (App1D if is1d else App2D)(pde_cls=pde_cls, nn_cls=dense_cls, plotter_cls=plot_cls)
         ms_d, loss_d = run(dense, args, a.steps)
-        out[name] = {"fused_ms_per_step": ms_f, "dense_eager_same_gpu_ms_per_step": ms_d,
-                     "speedup": ms_d / ms_f, "loss_fused": loss_f, "loss_dense": loss_d}
+        out[name] = {"fused_ms_per_step": ms_f, "fused_graphed_ms_per_step": ms_g,
+                     "dense_eager_same_gpu_ms_per_step": ms_d,
+                     "speedup_eager": ms_d / ms_f, "speedup_graphed": ms_d / ms_g,
+                     "loss_fused": loss_f, "loss_graphed": loss_g, "loss_dense": loss_d}
         print(name, json.dumps(out[name]), flush=True)
     print(json.dumps(out))
 
