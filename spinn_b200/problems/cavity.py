@@ -51,6 +51,14 @@ class CavityPDE(RegularPDE):
         self.rng_interior = np.arange(self.n_interior)
         self.sample_size = int(self.sample_frac * self.n_interior)
 
+    def enable_static_sampling(self):
+        """CUDA-graph mode: besides the static index buffer, cut the persistent autograd graph
+        of b_samples (a cat() of leaf tensors built once, cavity.py:62-65 -- the reason the
+        reference needs retain_graph=True): its AccumulateGrad nodes live on the legacy stream
+        and cannot be replayed inside a capture.  Same values, fresh leaves."""
+        super().enable_static_sampling()
+        self.b_samples = tuple(t.detach().clone().requires_grad_(True) for t in self.b_samples)
+
     def _compute_gradient(self, u, xs, ys):
         return derivs.grad_xy(u, xs, ys)
 

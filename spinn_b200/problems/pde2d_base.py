@@ -88,7 +88,11 @@ class RegularPDE(PDE):
             return
         import torch
         dev = self.p_samples[0].device
-        self._idx_host = torch.empty(self.sample_size, dtype=torch.int64).pin_memory()
+        # ring of pinned staging buffers: the host runs ahead of the GPU in graph mode, so a
+        # buffer may only be rewritten once the copy that read it has completed
+        self._idx_ring = [(torch.empty(self.sample_size, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+                          for _ in range(4)]
+        self._idx_turn = 0
         self._idx_dev = torch.zeros(self.sample_size, dtype=torch.int64, device=dev)
 
     def graph_pre_step(self):
@@ -96,8 +100,13 @@ class RegularPDE(PDE):
             return
         import torch
         idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        self._idx_host.copy_(torch.from_numpy(idx))
-        self._idx_dev.copy_(self._idx_host, non_blocking=True)
+        host, ev = self._idx_ring[self._idx_turn % len(self._idx_ring)]
+        if self._idx_turn >= len(self._idx_ring):
+            ev.synchronize()
+        self._idx_turn += 1
+        host.copy_(torch.from_numpy(idx))
+        self._idx_dev.copy_(host, non_blocking=True)
+        ev.record()
 
     def boundary(self):
         return self.b_samples
