@@ -278,7 +278,7 @@ def run_ours(args):
 
     def bwd_only():
         p = step.pack
-        rc = lib.spinn2d_jets_bwd(nn.kind, 2, n_loc, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y),
+        rc = lib.spinn2d_jets_bwd(nn.kind, 2, step.upstream_mask, n_loc, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y),
                                   P(l1.xf), P(l1.yf), P(l1.h), hs, P(l2.weight), P(step.gjets),
                                   P(p.view("d_x")), P(p.view("d_y")), P(p.view("d_h")), P(p.view("d_W")),
                                   P(p.view("d_b")), P(step.ws_b), step.ws_b.numel(), S())

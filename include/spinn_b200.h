@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SPINN_ABI_VERSION 1
+#define SPINN_ABI_VERSION 2
 #define SPINN_MAX_K 4
 
 #define SPINN_KIND_GAUSSIAN 0
@@ -72,9 +72,14 @@ int spinn2d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K,
 
 /* ---- 2-D backward: replaces loss.backward() through that graph (common.py:242-248).
  * d_xc/d_yc: [M_free]; d_h: [M] or [1]; d_W: [K][M]; d_bias: [K] or NULL.  Outputs are
- * overwritten (not accumulated). */
+ * overwritten (not accumulated).
+ * present_mask: bit a set <=> row a of gjets holds an upstream gradient; rows whose bit is
+ * clear count as zero and are NEVER READ (autograd's `None` for jets the loss does not use);
+ * 0 means "all rows of the level".  The structure is exploited: e.g. a Laplacian-type
+ * residual (only u_xx,u_yy: mask 0x18) or a Dirichlet penalty (only u: mask 0x01) run
+ * specialised per-pair code with fewer instructions -- results are those of the full formula. */
 size_t spinn2d_bwd_workspace_bytes(int N, int M, int K);
-int spinn2d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+int spinn2d_jets_bwd(int kind, int level, int present_mask, int N, int M_free, int M_fixed, int K,
                      const float* x, const float* y,
                      const float* xc_free, const float* yc_free,
                      const float* xc_fixed, const float* yc_fixed,
@@ -91,7 +96,7 @@ int spinn1d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K,
                      const float* W, const float* bias,
                      float* jets, void* workspace, size_t workspace_bytes, void* stream);
 size_t spinn1d_bwd_workspace_bytes(int N, int M, int K);
-int spinn1d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K,
+int spinn1d_jets_bwd(int kind, int level, int present_mask, int N, int M_free, int M_fixed, int K,
                      const float* x, const float* xc_free, const float* xc_fixed,
                      const float* h, int h_is_scalar,
                      const float* W, const float* gjets,

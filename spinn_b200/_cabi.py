@@ -24,11 +24,11 @@ SIGNATURES = {
     "spinn2d_fwd_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
     "spinn2d_jets_fwd": (_c_int, [_c_int] * 6 + [_c_fp] * 7 + [_c_int] + [_c_fp] * 4 + [_c_size, _c_fp]),
     "spinn2d_bwd_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
-    "spinn2d_jets_bwd": (_c_int, [_c_int] * 6 + [_c_fp] * 7 + [_c_int] + [_c_fp] * 8 + [_c_size, _c_fp]),
+    "spinn2d_jets_bwd": (_c_int, [_c_int] * 7 + [_c_fp] * 7 + [_c_int] + [_c_fp] * 8 + [_c_size, _c_fp]),
     "spinn1d_fwd_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
     "spinn1d_jets_fwd": (_c_int, [_c_int] * 6 + [_c_fp] * 4 + [_c_int] + [_c_fp] * 4 + [_c_size, _c_fp]),
     "spinn1d_bwd_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
-    "spinn1d_jets_bwd": (_c_int, [_c_int] * 6 + [_c_fp] * 4 + [_c_int] + [_c_fp] * 7 + [_c_size, _c_fp]),
+    "spinn1d_jets_bwd": (_c_int, [_c_int] * 7 + [_c_fp] * 4 + [_c_int] + [_c_fp] * 7 + [_c_size, _c_fp]),
     "spinn2d_poisson_residual_workspace_bytes": (_c_size, [_c_int]),
     "spinn2d_poisson_residual": (_c_int, [_c_int, ctypes.c_double] + [_c_fp] * 3 + [ctypes.c_float] * 5
                                  + [_c_fp] * 3 + [_c_size, _c_fp]),
@@ -36,6 +36,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 class SpinnNativeError(RuntimeError):
@@ -56,7 +57,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.spinn_abi_version() != 1:
+    if lib.spinn_abi_version() != ABI_VERSION:
         raise SpinnNativeError("libspinn_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -126,11 +126,16 @@ __global__ void pack_nodes_g2fwd_kernel(int M, int Mfree, int npairs,
   recs[3 * (size_t)p + 2] = make_float4(n[0].w1, n[1].w1, n[0].w2, n[1].w2);
 }
 
-// fast backward records: one per POINT PAIR (i, i+1), four float4:
-//   {x_i,x_i1,y_i,y_i1} {g0,g0',g1,g1'} {g2,g2',g3,g3'} {g4,g4',0,0}
+// fast backward records: one per POINT PAIR (i, i+1), bwd_nrec(MODE) float4 each:
+//   BWD_ALL : {x_i,x_i1,y_i,y_i1} {g0,g0',g1,g1'} {g2,g2',g3,g3'} {g4,g4',0,0}
+//   BWD_LAPL: {x..,y..} {g3,g3',g4,g4'} {g3+g4,(g3+g4)',0,0}
+//   BWD_U   : {x..,y..} {g0,g0',0,0}
+// rows of g whose bit in `mask` is clear are never read (they count as zero).
+template <int MODE>
 __global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict__ x,
                                          const float* __restrict__ y, const float* __restrict__ g,
-                                         float4* __restrict__ recs) {
+                                         int mask, float4* __restrict__ recs) {
+  constexpr int NREC = bwd_nrec(MODE);
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N2) return;
   int i0 = 2 * p, i1 = 2 * p + 1;
@@ -141,13 +146,23 @@ __global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict_
   float a[5], b[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    a[k] = g[k * n + i0];
-    b[k] = v1 ? g[k * n + i1] : 0.f;
+    const bool need = (MODE == BWD_ALL) || (MODE == BWD_LAPL && k >= 3) || (MODE == BWD_U && k == 0);
+    const bool have = need && ((mask >> k) & 1);
+    a[k] = have ? g[k * n + i0] : 0.f;
+    b[k] = (have && v1) ? g[k * n + i1] : 0.f;
   }
-  recs[4 * (size_t)p + 0] = make_float4(x0, x1, y0, y1);
-  recs[4 * (size_t)p + 1] = make_float4(a[0], b[0], a[1], b[1]);
-  recs[4 * (size_t)p + 2] = make_float4(a[2], b[2], a[3], b[3]);
-  recs[4 * (size_t)p + 3] = make_float4(a[4], b[4], 0.f, 0.f);
+  float4* r = recs + (size_t)NREC * p;
+  r[0] = make_float4(x0, x1, y0, y1);
+  if (MODE == BWD_ALL) {
+    r[1] = make_float4(a[0], b[0], a[1], b[1]);
+    r[2] = make_float4(a[2], b[2], a[3], b[3]);
+    r[3 % NREC] = make_float4(a[4], b[4], 0.f, 0.f);
+  } else if (MODE == BWD_LAPL) {
+    r[1] = make_float4(a[3], b[3], a[4], b[4]);
+    r[2 % NREC] = make_float4(a[3] + a[4], b[3] + b[4], 0.f, 0.f);
+  } else {
+    r[1] = make_float4(a[0], b[0], 0.f, 0.f);
+  }
 }
 
 // -----------------------------------------------------------------------------
@@ -160,31 +175,17 @@ static const FwdCfg FWD_CFGS[] = {
     {4, 256, 2, 2},   // 0
     {2, 512, 2, 2},   // 1
     {1, 512, 2, 4},   // 2
-    {2, 384, 2, 2},   // 3
-    {8, 128, 2, 1},   // 4
-    {4, 256, 2, 1},   // 5
-    {2, 256, 2, 4},   // 6
-    {4, 256, 2, 2},   // 7  all scalar
-    {4, 256, 2, 2},   // 8  packed geometry, scalar accumulation
-    {2, 512, 2, 2},   // 9  all scalar, more warps
-    {4, 256, 2, 2},   // 10 scalar geometry, packed accumulation
+    {2, 256, 2, 4},   // 3  (default: best on B200 at 4M and 512K points, tools/tune.py)
 };
 static const BwdCfg BWD_CFGS[] = {
     {2, 128, 4, 256},  // 0
     {1, 128, 8, 256},  // 1
-    {2, 256, 2, 256},  // 2
+    {2, 256, 2, 256},  // 2  (default)
     {4, 128, 2, 256},  // 3
-    {2, 128, 4, 512},  // 4
-    {1, 256, 4, 256},  // 5
-    {1, 128, 6, 512},  // 6
-    {2, 128, 4, 256},  // 7  all scalar
-    {2, 128, 4, 256},  // 8  packed math, scalar accumulation
-    {1, 128, 8, 256},  // 9  all scalar, more warps
-    {2, 128, 4, 256},  // 10 scalar math, packed accumulation
 };
 constexpr int N_FWD_CFGS = sizeof(FWD_CFGS) / sizeof(FWD_CFGS[0]);
 constexpr int N_BWD_CFGS = sizeof(BWD_CFGS) / sizeof(BWD_CFGS[0]);
-constexpr int FWD_DEFAULT = 6, BWD_DEFAULT = 2, WAVES_DEFAULT = 2;   // picked with tools/tune.py on B200
+constexpr int FWD_DEFAULT = 3, BWD_DEFAULT = 2, WAVES_DEFAULT = 2;   // picked with tools/tune.py on B200
 
 struct Tune { int fwd, bwd, waves; };
 static Tune get_tune() {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void store_points(float* __restrict__ p, long long i0
     if (i0 + q < N) p[i0 + q] = v[q];
 }
 
-template <int P, bool MIXED, int UNROLL, int PK, int PA>
+template <int P, bool MIXED, int UNROLL>
 __device__ __forceinline__ void g2k1_fwd_inner(const float4* __restrict__ sm4, int n,
                                                const float2* x2, const float2* y2,
                                                float2 (*acc)[MIXED ? 6 : 5]) {
@@ -262,11 +263,11 @@ __device__ __forceinline__ void g2k1_fwd_inner(const float4* __restrict__ sm4, i
     const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
     const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
 #pragma unroll
-    for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED, PK, PA>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+    for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
   }
 }
 
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, int PK, int PA>
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
@@ -308,14 +309,14 @@ g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
       for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
     }
     if (single) {
-      g2k1_fwd_inner<P, MIXED, UNROLL, PK, PA>(sm4, npairs, x2, y2, acc);
+      g2k1_fwd_inner<P, MIXED, UNROLL>(sm4, npairs, x2, y2, acc);
     } else {
       for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
         const int n = min(tile_pairs, npairs - t0);
         __syncthreads();
         for (int e = threadIdx.x; e < 3 * n; e += THREADS) sm4[e] = recs[3 * (size_t)t0 + e];
         __syncthreads();
-        g2k1_fwd_inner<P, MIXED, UNROLL, PK, PA>(sm4, n, x2, y2, acc);
+        g2k1_fwd_inner<P, MIXED, UNROLL>(sm4, n, x2, y2, acc);
       }
     }
     if (active) {
@@ -338,11 +339,12 @@ g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
 // Two-level accumulation (per tile, then per chunk) keeps fp32 round-off at the
 // level of the reference's pairwise torch.sum.
 // -----------------------------------------------------------------------------
-template <int Q, int THREADS, int MINB, int TILE, int PK, int PA>
+template <int Q, int THREADS, int MINB, int TILE, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
                 const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
-  __shared__ float4 sm4[4 * TILE];
+  constexpr int NREC = bwd_nrec(MODE), NACC = bwd_nacc(MODE);
+  __shared__ float4 sm4[NREC * TILE];
   const int jbase = blockIdx.x * (Q * THREADS) + threadIdx.x;
   float2 nc[Q], nd[Q], rp[Q], nrt[Q], rho[Q], nk1[Q], k2p[Q];
   float hq[Q], wq[Q];
@@ -356,39 +358,52 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
     nc[q] = f2dup(n.nc); nd[q] = f2dup(n.nd); rp[q] = f2dup(n.rp); nrt[q] = f2dup(n.nrt);
     rho[q] = f2dup(n.rho); nk1[q] = f2dup(n.nk1); k2p[q] = f2dup(n.k2p);
   }
-  float tot[Q][4];
+  float tot[Q][NACC];
 #pragma unroll
   for (int q = 0; q < Q; ++q)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) tot[q][a] = 0.f;
+    for (int a = 0; a < NACC; ++a) tot[q][a] = 0.f;
 
   const int p_begin = blockIdx.y * pairs_per_chunk;
   const int p_end = min(N2, p_begin + pairs_per_chunk);
   for (int t0 = p_begin; t0 < p_end; t0 += TILE) {
     const int n = min(TILE, p_end - t0);
     __syncthreads();
-    for (int e = threadIdx.x; e < 4 * n; e += THREADS) sm4[e] = ptrecs[4 * (size_t)t0 + e];
+    for (int e = threadIdx.x; e < NREC * n; e += THREADS) sm4[e] = ptrecs[NREC * (size_t)t0 + e];
     __syncthreads();
-    float2 acc[Q][4];
+    float2 acc[Q][NACC];
 #pragma unroll
     for (int q = 0; q < Q; ++q)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) acc[q][a] = f2(0.f, 0.f);
+      for (int a = 0; a < NACC; ++a) acc[q][a] = f2(0.f, 0.f);
 #pragma unroll 2
     for (int p = 0; p < n; ++p) {
-      const float4 A = sm4[4 * p + 0], B = sm4[4 * p + 1], C = sm4[4 * p + 2], D = sm4[4 * p + 3];
+      const float4 A = sm4[NREC * p + 0], B = sm4[NREC * p + 1];
       const float2 x2 = f2(A.x, A.y), y2 = f2(A.z, A.w);
-      const float2 g0 = f2(B.x, B.y), g1 = f2(B.z, B.w), g2 = f2(C.x, C.y), g3 = f2(C.z, C.w);
-      const float2 g4 = f2(D.x, D.y);
+      if (MODE == BWD_ALL) {
+        const float4 C = sm4[NREC * p + 2 % NREC], D = sm4[NREC * p + 3 % NREC];
+        const float2 g0 = f2(B.x, B.y), g1 = f2(B.z, B.w), g2 = f2(C.x, C.y), g3 = f2(C.z, C.w);
+        const float2 g4 = f2(D.x, D.y);
 #pragma unroll
-      for (int q = 0; q < Q; ++q)
-        g2_bwd_pair<PK, PA>(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q],
-                    acc[q]);
+        for (int q = 0; q < Q; ++q)
+          g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q],
+                              k2p[q], acc[q]);
+      } else if (MODE == BWD_LAPL) {
+        const float2 C = *reinterpret_cast<const float2*>(&sm4[NREC * p + 2 % NREC]);
+        const float2 g3 = f2(B.x, B.y), g4 = f2(B.z, B.w);
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          g2_bwd_pair_lapl(x2, y2, g3, g4, C, nc[q], nd[q], rp[q], acc[q]);
+      } else {
+        const float2 g0 = f2(B.x, B.y);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g2_bwd_pair_u(x2, y2, g0, nc[q], nd[q], rp[q], acc[q]);
+      }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
+      for (int a = 0; a < NACC; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
   }
   // rows: 0 dc, 1 dd, 2 dh, 3 dW
   float* out = partials + (size_t)blockIdx.y * 4 * Mp;
@@ -396,7 +411,7 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
   for (int q = 0; q < Q; ++q) {
     const int j = jbase + q * THREADS;
     float dW, dc, dd, dh;
-    g2_bwd_finish(hq[q], wq[q], tot[q][0], tot[q][1], tot[q][2], tot[q][3], &dW, &dc, &dd, &dh);
+    g2_bwd_finish_m<MODE>(hq[q], wq[q], tot[q], &dW, &dc, &dd, &dh);
     out[j] = dc;
     out[(size_t)Mp + j] = dd;
     out[2 * (size_t)Mp + j] = dh;
@@ -464,7 +479,7 @@ fwd_generic_kernel(int N, int Mp, const float* __restrict__ x, const float* __re
 template <int DIM, int KIND, int K, int LEVEL>
 __global__ void __launch_bounds__(GEN_THREADS)
 bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x,
-                   const float* __restrict__ y, const float* __restrict__ gj,
+                   const float* __restrict__ y, const float* __restrict__ gj, int mask,
                    const float* __restrict__ soa, float* __restrict__ partials) {
   constexpr int NG = njets(DIM, LEVEL);
   constexpr int TP = GEN_TILE_POINTS;
@@ -495,7 +510,8 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
 #pragma unroll
       for (int a = 0; a < NG; ++a)
 #pragma unroll
-        for (int k = 0; k < K; ++k) sg[(a * K + k) * TP + e] = gj[((size_t)a * N + t0 + e) * K + k];
+        for (int k = 0; k < K; ++k)
+          sg[(a * K + k) * TP + e] = ((mask >> a) & 1) ? gj[((size_t)a * N + t0 + e) * K + k] : 0.f;
     }
     __syncthreads();
     float acc[NACC];
@@ -691,7 +707,19 @@ struct BwdPlan {
 };
 
 static bool bwd_is_fast(int dim, int kind, int level, int K) {
-  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && level == 2;
+  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && level <= 2;
+}
+
+// effective upstream mask: bit a set <=> row a of gjets is present; 0 on input means "all"
+static int effective_mask(int dim, int level, int present_mask) {
+  const int all = (1 << njets(dim, level)) - 1;
+  return present_mask == 0 ? all : (present_mask & all);
+}
+
+static int bwd_mode_for(int mask) {
+  if (mask == 0x01) return BWD_U;
+  if ((mask & ~0x18) == 0) return BWD_LAPL;
+  return BWD_ALL;
 }
 
 // chunking: enough (node group x point chunk) blocks for `waves` waves of resident CTAs
@@ -786,29 +814,29 @@ static void launch_fwd_generic_k(int K, int level, int N, int Mp, const float* x
 
 template <int DIM, int KIND, int K>
 static void launch_bwd_generic_level(int level, dim3 grid, int N, int Mp, int per_chunk,
-                                     const float* x, const float* y, const float* gj,
+                                     const float* x, const float* y, const float* gj, int mask,
                                      const float* soa, float* partials, cudaStream_t s) {
   dim3 block(GEN_THREADS);
   switch (level) {
-    case 0: bwd_generic_kernel<DIM, KIND, K, 0><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
-    case 1: bwd_generic_kernel<DIM, KIND, K, 1><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
-    case 2: bwd_generic_kernel<DIM, KIND, K, 2><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials); break;
+    case 0: bwd_generic_kernel<DIM, KIND, K, 0><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, mask, soa, partials); break;
+    case 1: bwd_generic_kernel<DIM, KIND, K, 1><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, mask, soa, partials); break;
+    case 2: bwd_generic_kernel<DIM, KIND, K, 2><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, mask, soa, partials); break;
     default:
       if (DIM == 2)
-        bwd_generic_kernel<DIM, KIND, K, (DIM == 2 ? 3 : 2)><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, soa, partials);
+        bwd_generic_kernel<DIM, KIND, K, (DIM == 2 ? 3 : 2)><<<grid, block, 0, s>>>(N, Mp, per_chunk, x, y, gj, mask, soa, partials);
       break;
   }
 }
 
 template <int DIM, int KIND>
 static void launch_bwd_generic_k(int K, int level, dim3 grid, int N, int Mp, int per_chunk,
-                                 const float* x, const float* y, const float* gj, const float* soa,
-                                 float* partials, cudaStream_t s) {
+                                 const float* x, const float* y, const float* gj, int mask,
+                                 const float* soa, float* partials, cudaStream_t s) {
   switch (K) {
-    case 1: launch_bwd_generic_level<DIM, KIND, 1>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
-    case 2: launch_bwd_generic_level<DIM, KIND, 2>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
-    case 3: launch_bwd_generic_level<DIM, KIND, 3>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
-    default: launch_bwd_generic_level<DIM, KIND, 4>(level, grid, N, Mp, per_chunk, x, y, gj, soa, partials, s); break;
+    case 1: launch_bwd_generic_level<DIM, KIND, 1>(level, grid, N, Mp, per_chunk, x, y, gj, mask, soa, partials, s); break;
+    case 2: launch_bwd_generic_level<DIM, KIND, 2>(level, grid, N, Mp, per_chunk, x, y, gj, mask, soa, partials, s); break;
+    case 3: launch_bwd_generic_level<DIM, KIND, 3>(level, grid, N, Mp, per_chunk, x, y, gj, mask, soa, partials, s); break;
+    default: launch_bwd_generic_level<DIM, KIND, 4>(level, grid, N, Mp, per_chunk, x, y, gj, mask, soa, partials, s); break;
   }
 }
 
@@ -856,13 +884,13 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const bool mixed = level == 3;
     const Tune tune = get_tune();
     const int sms = sm_count();
-#define SPINN_LAUNCH_FAST_FWD(P_, T_, B_, U_, PK_, PA_)                                                     \
+#define SPINN_LAUNCH_FAST_FWD(P_, T_, B_, U_)                                                               \
   do {                                                                                              \
     const long long nwt = ((long long)N + 32 * P_ - 1) / (32 * P_);                                 \
     long long blocks = (nwt + (T_ / 32) - 1) / (T_ / 32);                                           \
     if (blocks > (long long)sms * B_) blocks = (long long)sms * B_;                                 \
     if (mixed) {                                                                                    \
-      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_, PK_, PA_>;                                   \
+      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_>;                                             \
       static bool configured = false; /* once per instantiation: not during graph capture */       \
       if (!configured) {                                                                            \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
@@ -870,7 +898,7 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
       }                                                                                             \
       kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
     } else {                                                                                        \
-      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_, PK_, PA_>;                                  \
+      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_>;                                            \
       static bool configured = false;                                                               \
       if (!configured) {                                                                            \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
@@ -883,17 +911,10 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const bool small = (long long)N < (long long)32 * 4 * 8 * sms;
     const int v = small ? 2 : tune.fwd;
     switch (v) {
-      case 0: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 1, 1); break;
-      case 1: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2, 1, 1); break;
-      case 2: SPINN_LAUNCH_FAST_FWD(1, 512, 2, 4, 1, 1); break;
-      case 3: SPINN_LAUNCH_FAST_FWD(2, 384, 2, 2, 1, 1); break;
-      case 4: SPINN_LAUNCH_FAST_FWD(8, 128, 2, 1, 1, 1); break;
-      case 5: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 1, 1, 1); break;
-      case 6: SPINN_LAUNCH_FAST_FWD(2, 256, 2, 4, 1, 1); break;
-      case 7: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 0, 0); break;
-      case 8: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 1, 0); break;
-      case 9: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2, 0, 0); break;
-      default: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2, 0, 1); break;
+      case 0: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2); break;
+      case 1: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2); break;
+      case 2: SPINN_LAUNCH_FAST_FWD(1, 512, 2, 4); break;
+      default: SPINN_LAUNCH_FAST_FWD(2, 256, 2, 4); break;
     }
 #undef SPINN_LAUNCH_FAST_FWD
     LAUNCH_CHECK("g2k1_fwd_kernel");
@@ -917,8 +938,8 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
   return SPINN_OK;
 }
 
-static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_fixed, int K,
-                         const float* x, const float* y, const float* xf, const float* yf,
+static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, int M_free,
+                         int M_fixed, int K, const float* x, const float* y, const float* xf, const float* yf,
                          const float* xfix, const float* yfix, const float* h, int hs,
                          const float* W, const float* gj, float* d_xc, float* d_yc, float* d_h,
                          float* d_W, float* d_bias, void* ws, size_t ws_bytes, void* stream) {
@@ -940,8 +961,10 @@ static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_
   float* bpart = (float*)(base + p.off_bias);
   float* htmp = (float*)(base + p.off_htmp);
   const int nacc = dim + 1 + K;
+  if (present_mask < 0) return fail(SPINN_E_BADARG, "present_mask must be >= 0");
+  const int mask = effective_mask(dim, level, present_mask);
 
-  if (N == 0) {  // empty point set: all gradients are zero
+  if (N == 0 || mask == 0) {  // empty point set or no upstream gradient: all gradients are zero
     if (M_free) CUDA_TRY(cudaMemsetAsync(d_xc, 0, sizeof(float) * M_free, s));
     if (dim == 2 && M_free) CUDA_TRY(cudaMemsetAsync(d_yc, 0, sizeof(float) * M_free, s));
     CUDA_TRY(cudaMemsetAsync(d_h, 0, sizeof(float) * (hs ? 1 : M), s));
@@ -959,37 +982,41 @@ static int jets_bwd_impl(int dim, int kind, int level, int N, int M_free, int M_
   dim3 grid(p.node_groups, p.chunks);
   if (p.fast) {
     float4* ptrecs = (float4*)(base + p.off_pts);
-    pack_points_g2bwd_kernel<<<ceil_div_i(p.N2, 256), 256, 0, s>>>(N, p.N2, x, y, gj, ptrecs);
+    const int mode = bwd_mode_for(mask);
+    const int pgrid = ceil_div_i(p.N2, 256);
+    if (mode == BWD_ALL) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    else if (mode == BWD_LAPL) pack_points_g2bwd_kernel<BWD_LAPL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    else pack_points_g2bwd_kernel<BWD_U><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     LAUNCH_CHECK("pack_points_g2bwd_kernel");
-#define SPINN_LAUNCH_FAST_BWD(Q_, T_, B_, TILE_, PK_, PA_) \
-  g2k1_bwd_kernel<Q_, T_, B_, TILE_, PK_, PA_><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials)
+#define SPINN_LAUNCH_FAST_BWD(Q_, T_, B_, TILE_)                                                              \
+  do {                                                                                                        \
+    if (mode == BWD_ALL)                                                                                      \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_ALL><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);  \
+    else if (mode == BWD_LAPL)                                                                                \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_LAPL><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else                                                                                                      \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_U><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);    \
+  } while (0)
     switch (p.variant) {
-      case 0: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 1, 1); break;
-      case 1: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256, 1, 1); break;
-      case 2: SPINN_LAUNCH_FAST_BWD(2, 256, 2, 256, 1, 1); break;
-      case 3: SPINN_LAUNCH_FAST_BWD(4, 128, 2, 256, 1, 1); break;
-      case 4: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 512, 1, 1); break;
-      case 5: SPINN_LAUNCH_FAST_BWD(1, 256, 4, 256, 1, 1); break;
-      case 6: SPINN_LAUNCH_FAST_BWD(1, 128, 6, 512, 1, 1); break;
-      case 7: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 0, 0); break;
-      case 8: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 1, 0); break;
-      case 9: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256, 0, 0); break;
-      default: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256, 0, 1); break;
+      case 0: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256); break;
+      case 1: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256); break;
+      case 3: SPINN_LAUNCH_FAST_BWD(4, 128, 2, 256); break;
+      default: SPINN_LAUNCH_FAST_BWD(2, 256, 2, 256); break;
     }
 #undef SPINN_LAUNCH_FAST_BWD
     LAUNCH_CHECK("g2k1_bwd_kernel");
   } else {
     if (dim == 2) {
-      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<2, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, soa, partials, s);
-      else launch_bwd_generic_k<2, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, soa, partials, s);
+      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<2, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, mask, soa, partials, s);
+      else launch_bwd_generic_k<2, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, y, gj, mask, soa, partials, s);
     } else {
-      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<1, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, soa, partials, s);
-      else launch_bwd_generic_k<1, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, soa, partials, s);
+      if (kind == SPINN_KIND_GAUSSIAN) launch_bwd_generic_k<1, GAUSSIAN>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, mask, soa, partials, s);
+      else launch_bwd_generic_k<1, SOFTPLUS>(K, level, grid, N, p.Mp, p.per_chunk, x, nullptr, gj, mask, soa, partials, s);
     }
     LAUNCH_CHECK("bwd_generic_kernel");
   }
   int nb = 0;
-  if (d_bias) {
+  if (d_bias && (mask & 1)) {
     nb = ceil_div_i(N, 256) < BIAS_BLOCKS ? ceil_div_i(N, 256) : BIAS_BLOCKS;
     bias_partial_kernel<<<nb, 256, 0, s>>>(N, K, gj, bpart);
     LAUNCH_CHECK("bias_partial_kernel");
@@ -1045,22 +1072,22 @@ int spinn1d_jets_fwd(int kind, int level, int N, int M_free, int M_fixed, int K,
                        nullptr, h, h_is_scalar, W, bias, jets, workspace, workspace_bytes, stream);
 }
 
-int spinn2d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+int spinn2d_jets_bwd(int kind, int level, int present_mask, int N, int M_free, int M_fixed, int K, const float* x,
                      const float* y, const float* xc_free, const float* yc_free,
                      const float* xc_fixed, const float* yc_fixed, const float* h, int h_is_scalar,
                      const float* W, const float* gjets, float* d_xc, float* d_yc, float* d_h,
                      float* d_W, float* d_bias, void* workspace, size_t workspace_bytes,
                      void* stream) {
-  return jets_bwd_impl(2, kind, level, N, M_free, M_fixed, K, x, y, xc_free, yc_free, xc_fixed,
+  return jets_bwd_impl(2, kind, level, present_mask, N, M_free, M_fixed, K, x, y, xc_free, yc_free, xc_fixed,
                        yc_fixed, h, h_is_scalar, W, gjets, d_xc, d_yc, d_h, d_W, d_bias, workspace,
                        workspace_bytes, stream);
 }
 
-int spinn1d_jets_bwd(int kind, int level, int N, int M_free, int M_fixed, int K, const float* x,
+int spinn1d_jets_bwd(int kind, int level, int present_mask, int N, int M_free, int M_fixed, int K, const float* x,
                      const float* xc_free, const float* xc_fixed, const float* h, int h_is_scalar,
                      const float* W, const float* gjets, float* d_xc, float* d_h, float* d_W,
                      float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
-  return jets_bwd_impl(1, kind, level, N, M_free, M_fixed, K, x, nullptr, xc_free, nullptr, xc_fixed,
+  return jets_bwd_impl(1, kind, level, present_mask, N, M_free, M_fixed, K, x, nullptr, xc_free, nullptr, xc_fixed,
                        nullptr, h, h_is_scalar, W, gjets, d_xc, nullptr, d_h, d_W, d_bias, workspace,
                        workspace_bytes, stream);
 }

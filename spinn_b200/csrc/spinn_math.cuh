@@ -217,6 +217,86 @@ SP_HD void g2_bwd_finish(float h, float W, float aW, float nAc, float nAd, float
   *dh = (float)(f / SIG_D * (double)nAh);
 }
 
+// ---- backward specialisations on the STRUCTURE of the upstream gradient ------------------
+// Autograd hands the fused op `None` for every jet the loss does not depend on (exactly the
+// paths the reference's own backward never walks).  Two patterns are common enough to get their
+// own per-pair code: only (u_xx, u_yy) present -- Laplacian-type residuals such as the Poisson
+// configs -- and only u present -- Dirichlet boundary penalties.  With the absent terms removed
+// every remaining term shares one node-constant factor, which moves out of the sum over points.
+enum { BWD_ALL = 0, BWD_LAPL = 1, BWD_U = 2 };
+SP_HD constexpr int bwd_nrec(int mode) { return mode == BWD_ALL ? 4 : mode == BWD_LAPL ? 3 : 2; }
+SP_HD constexpr int bwd_nacc(int mode) { return mode == BWD_ALL ? 4 : mode == BWD_LAPL ? 5 : 4; }
+
+// only g3 (u_xx), g4 (u_yy) and g34 = g3+g4:  q = g3 hx + g4 hy
+//   acc0 += E q;  acc1 += E xi (q - 2 s2 g3);  acc2 += E eta (q - 2 s2 g4);
+//   acc3 += E q (t - 2 s2);  acc4 += E g34            (s2 = sigma^2)
+template <int PK = 1, int PA = 1>
+SP_HD void g2_bwd_pair_lapl(float2 x2, float2 y2, float2 g3, float2 g4, float2 g34,
+                            float2 nc, float2 nd, float2 rp, float2* acc) {
+  const float2 nsig2 = f2dup(-SIG2_F), n2sig2 = f2dup(-2.0f * SIG2_F);
+  float2 X  = f2add<PK>(x2, nc);
+  float2 Y  = f2add<PK>(y2, nd);
+  float2 xi = f2mul<PK>(X, rp);
+  float2 et = f2mul<PK>(Y, rp);
+  float2 hx = f2fma<PK>(xi, xi, nsig2);
+  float2 hy = f2fma<PK>(et, et, nsig2);
+  float2 t  = f2add<PK>(hx, hy);
+  float2 E  = f2ex2neg(t);
+  float2 q  = f2mul<PK>(g3, hx);
+  q = f2fma<PK>(g4, hy, q);
+  float2 Eq = f2mul<PK>(E, q);
+  float2 cx = f2fma<PK>(n2sig2, g3, q);
+  float2 cy = f2fma<PK>(n2sig2, g4, q);
+  float2 Ex = f2mul<PK>(E, xi);
+  float2 Ey = f2mul<PK>(E, et);
+  float2 u  = f2add<PK>(t, n2sig2);
+  acc[0] = f2add<PA>(acc[0], Eq);
+  acc[1] = f2fma<PA>(Ex, cx, acc[1]);
+  acc[2] = f2fma<PA>(Ey, cy, acc[2]);
+  acc[3] = f2fma<PA>(Eq, u, acc[3]);
+  acc[4] = f2fma<PA>(E, g34, acc[4]);
+}
+
+// only g0 (u):  phi = 2^{-(xi^2+eta^2)} directly;  acc0 += phi g0; acc1 += phi g0 xi;
+//   acc2 += phi g0 eta;  acc3 += phi g0 (xi^2+eta^2)
+template <int PK = 1, int PA = 1>
+SP_HD void g2_bwd_pair_u(float2 x2, float2 y2, float2 g0, float2 nc, float2 nd, float2 rp,
+                         float2* acc) {
+  float2 X  = f2add<PK>(x2, nc);
+  float2 Y  = f2add<PK>(y2, nd);
+  float2 xi = f2mul<PK>(X, rp);
+  float2 et = f2mul<PK>(Y, rp);
+  float2 r2 = f2mul<PK>(xi, xi);
+  r2 = f2fma<PK>(et, et, r2);
+  float2 ph = f2ex2neg(r2);
+  float2 pg = f2mul<PK>(ph, g0);
+  acc[0] = f2add<PA>(acc[0], pg);
+  acc[1] = f2fma<PA>(pg, xi, acc[1]);
+  acc[2] = f2fma<PA>(pg, et, acc[2]);
+  acc[3] = f2fma<PA>(pg, r2, acc[3]);
+}
+
+template <int MODE>
+SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* dc, float* dd, float* dh) {
+  const double rt = 1.0 / (SIG_D * (double)h);
+  if (MODE == BWD_ALL) {
+    g2_bwd_finish(h, W, a[0], a[1], a[2], a[3], dW, dc, dd, dh);
+  } else if (MODE == BWD_LAPL) {
+    const double rho = rt * rt;
+    const double f = (double)W * rt * rho * INV_E_D;
+    *dW = (float)(rho * INV_E_D * (double)a[0]);
+    *dc = (float)(f * (double)a[1]);
+    *dd = (float)(f * (double)a[2]);
+    *dh = (float)(f / SIG_D * ((double)a[3] - 2.0 * SIG2_D * SIG2_D * (double)a[4]));
+  } else {
+    const double f = (double)W * rt;
+    *dW = a[0];
+    *dc = (float)(f * (double)a[1]);
+    *dd = (float)(f * (double)a[2]);
+    *dh = (float)(f / SIG_D * (double)a[3]);
+  }
+}
+
 // number of jets / upstream-gradient slots per "level"
 //   2-D: level 0: u | 1: u,ux,uy | 2: u,ux,uy,uxx,uyy | 3: + uxy
 //   1-D: level 0: u | 1: u,ux    | 2: u,ux,uxx

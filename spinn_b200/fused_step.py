@@ -24,7 +24,7 @@ class PoissonInteriorStep:
     #: pack_nodes(bwd), pack_points, bwd, bias_partial, finalize
     LAUNCHES = 9
 
-    def __init__(self, nn, x, y, n_total=None, residual=SINE):
+    def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True):
         if nn.layer2.weight.shape[0] != 1:
             raise ValueError("PoissonInteriorStep is for scalar problems (K=1)")
         self.lib = _cabi.load()
@@ -34,6 +34,9 @@ class PoissonInteriorStep:
         self.N = self.x.numel()
         self.n_total = float(self.N if n_total is None else n_total)
         self.res = dict(residual)
+        # dLoss/dJets of this residual is structurally zero for u, u_x, u_y: tell the backward
+        # (0x18 = rows u_xx, u_yy present); structured=False runs the general 5-row backward
+        self.upstream_mask = 0x18 if structured else 0
         l1, l2 = nn.layer1, nn.layer2
         dev = self.x.device
         self.Mf, self.Mx = l1.x.numel(), l1.xf.numel()
@@ -64,7 +67,7 @@ class PoissonInteriorStep:
                                           r["scale"], r["amp"], r["kx"], r["ky"], r["f0"], _ptr(self.gjets),
                                           _ptr(p.view("loss")), _ptr(self.ws_r), self.ws_r.numel(), s)
         _cabi.check(rc, "spinn2d_poisson_residual")
-        rc = lib.spinn2d_jets_bwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
+        rc = lib.spinn2d_jets_bwd(nn.kind, 2, self.upstream_mask, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
                                   _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
                                   _ptr(l2.weight), _ptr(self.gjets), _ptr(p.view("d_x")), _ptr(p.view("d_y")),
                                   _ptr(p.view("d_h")), _ptr(p.view("d_W")),

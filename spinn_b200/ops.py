@@ -90,7 +90,8 @@ class CudaBackend:
         _cabi.check(rc, f"spinn{dim}d_jets_fwd")
         return jets
 
-    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias):
+    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias, mask=0):
+        """mask: bit a set <=> gj[a] holds an upstream gradient (0 = all rows of the level)."""
         lib = _cabi.load()
         dev = self._check(x, y, xf, yf, xfix, yfix, h, W, gj)
         N = x.numel()
@@ -106,14 +107,14 @@ class CudaBackend:
             if dim == 2:
                 nbytes = lib.spinn2d_bwd_workspace_bytes(N, M, K)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                rc = lib.spinn2d_jets_bwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(y), _ptr(xf), _ptr(yf),
+                rc = lib.spinn2d_jets_bwd(kind, level, mask, N, Mf, Mx, K, _ptr(x), _ptr(y), _ptr(xf), _ptr(yf),
                                           _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1), _ptr(W),
                                           _ptr(gj), _ptr(d_xc), _ptr(d_yc), _ptr(d_h), _ptr(d_W), _ptr(d_b),
                                           _ptr(ws), nbytes, _stream())
             else:
                 nbytes = lib.spinn1d_bwd_workspace_bytes(N, M, K)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                rc = lib.spinn1d_jets_bwd(kind, level, N, Mf, Mx, K, _ptr(x), _ptr(xf), _ptr(xfix), _ptr(h),
+                rc = lib.spinn1d_jets_bwd(kind, level, mask, N, Mf, Mx, K, _ptr(x), _ptr(xf), _ptr(xfix), _ptr(h),
                                           int(h.numel() == 1), _ptr(W), _ptr(gj), _ptr(d_xc), _ptr(d_h),
                                           _ptr(d_W), _ptr(d_b), _ptr(ws), nbytes, _stream())
         _cabi.check(rc, f"spinn{dim}d_jets_bwd")
@@ -169,11 +170,14 @@ class _FusedJets(torch.autograd.Function):
         lv = _level_for(dim, present[-1])
         ng = num_jets(dim, lv)
         N, K = x.numel(), W.shape[0]
-        gj = torch.zeros((ng, N, K), dtype=torch.float32, device=x.device)
+        # rows of absent jets are never read by the kernels (present-mask): no zero fill
+        gj = torch.empty((ng, N, K), dtype=torch.float32, device=x.device)
+        mask = 0
         for i in present:
             gj[i].copy_(gs[i].reshape(N, K))
+            mask |= 1 << i
         d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward(
-            dim, kind, lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias)
+            dim, kind, lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias, mask)
         return (None, None, None, None, None, d_xc, d_yc, None, None,
                 d_h.reshape(ctx.h_shape), d_W, d_b)
 

@@ -67,12 +67,16 @@ class OracleBackend:
             J = cf.jets1d(kind, n(x), np.concatenate([n(xf), n(xfix)]), n(h), n(W), n(b))
         return torch.tensor(J[:nj], dtype=torch.float32, device=x.device)
 
-    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias):
+    def backward(self, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias, mask=0):
         import torch
         from oracle import closed_form as cf
         self.calls["backward"] += 1
         n = self._np
         g = n(gj)
+        if mask:                                   # rows whose bit is clear are undefined: zero them
+            for a in range(g.shape[0]):
+                if not (mask >> a) & 1:
+                    g[a] = 0.0
         full = 6 if dim == 2 else 3
         if g.shape[0] < full:
             g = np.concatenate([g, np.zeros((full - g.shape[0],) + g.shape[1:])], 0)

@@ -56,6 +56,34 @@ void hc_g2_bwd(int N, int M, const float* x, const float* y, const float* g, con
   }
 }
 
+// structured-upstream backward emulation: mode 1 (only g3,g4 given as g[0..1][N]) and
+// mode 2 (only g0 given as g[0][N]); outputs dc, dd, dh, dW [M]
+void hc_g2_bwd_mode(int mode, int N, int M, const float* x, const float* y, const float* g,
+                    const float* c, const float* d, const float* h, const float* W, float* dc,
+                    float* dd, float* dh, float* dW) {
+  int N2 = (N + 1) / 2;
+  for (int j = 0; j < M; ++j) {
+    G2BwdNode n = g2_bwd_node(c[j], d[j], h[j]);
+    float tot[5] = {0, 0, 0, 0, 0};
+    float2 acc[5];
+    for (int a = 0; a < 5; ++a) acc[a] = f2(0.f, 0.f);
+    for (int p = 0; p < N2; ++p) {
+      int i0 = 2 * p, i1 = 2 * p + 1;
+      bool v = i1 < N;
+      float2 x2 = f2(x[i0], v ? x[i1] : x[i0]), y2 = f2(y[i0], v ? y[i1] : y[i0]);
+      if (mode == 1) {
+        float2 g3 = f2(g[i0], v ? g[i1] : 0.f), g4 = f2(g[(size_t)N + i0], v ? g[(size_t)N + i1] : 0.f);
+        g2_bwd_pair_lapl(x2, y2, g3, g4, f2(g3.x + g4.x, g3.y + g4.y), f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), acc);
+      } else {
+        g2_bwd_pair_u(x2, y2, f2(g[i0], v ? g[i1] : 0.f), f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), acc);
+      }
+    }
+    for (int a = 0; a < 5; ++a) tot[a] = acc[a].x + acc[a].y;
+    if (mode == 1) g2_bwd_finish_m<BWD_LAPL>(h[j], W[j], tot, &dW[j], &dc[j], &dd[j], &dh[j]);
+    else g2_bwd_finish_m<BWD_U>(h[j], W[j], tot, &dW[j], &dc[j], &dd[j], &dh[j]);
+  }
+}
+
 }  // extern "C"
 
 template <int DIM, int KIND, int K, int LEVEL>

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 def test_loader_signatures_and_version():
     from spinn_b200 import _cabi
     lib = _cabi.load()
-    assert lib.spinn_abi_version() == 1
+    assert lib.spinn_abi_version() == _cabi.ABI_VERSION == 2
     assert lib.spinn_num_jets(2, 2) == 5 and lib.spinn_num_jets(2, 3) == 6 and lib.spinn_num_jets(1, 2) == 3
     assert lib.spinn_num_jets(1, 3) < 0
     # workspace sizing is pure host arithmetic (device query falls back to 148 SMs without a GPU)

@@ -46,7 +46,7 @@ def backend():
 def test_native_library_is_loaded_and_exports_abi():
     from spinn_b200 import _cabi
     lib = _cabi.load()
-    assert lib.spinn_abi_version() == 1
+    assert lib.spinn_abi_version() == _cabi.ABI_VERSION
     for name in _cabi.SIGNATURES:
         assert hasattr(lib, name)
 
@@ -284,3 +284,28 @@ def test_full_size_point_sharding_is_additive(full_state):
         acc += PoissonInteriorStep(nn, xs[lo:hi], ys[lo:hi], n_total=N).run(all_reduce=False).double()
     scale = whole.abs().max()
     assert float((acc - whole).abs().max() / scale) < 5e-6
+
+
+@pytest.mark.parametrize("mask", [0x18, 0x08, 0x10, 0x01, 0x19, 0x06, 0x1F])
+@pytest.mark.parametrize("kind,K", [("gaussian", 1), ("gaussian", 3), ("softplus", 1)])
+def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
+    """present_mask: absent rows of gjets count as zero and are never read (they hold NaN here);
+    the structured fast paths (0x18 Laplacian-type, 0x01 u-only) agree with the full formula."""
+    c = _random_problem(77 + mask, 2049, 301, 40, K)
+    c["kind"] = kind
+    be = backend()
+    g = c["gjets"][:5].copy()
+    g_dev = g.copy()
+    for a in range(5):
+        if not (mask >> a) & 1:
+            g[a] = 0.0
+            g_dev[a] = np.nan
+    args = (T(c["x"]), T(c["y"]), T(c["xf"]), T(c["yf"]), T(c["xfix"]), T(c["yfix"]), T(c["h"]), T(c["W"]))
+    grads = be.backward(2, cf.kind_id(kind), 2, *args, T(g_dev), True, mask)
+    xc = np.concatenate([c["xf"], c["xfix"]])
+    yc = np.concatenate([c["yf"], c["yfix"]])
+    G = cf.grads2d(kind, c["x"], c["y"], xc, yc, c["h"], c["W"], g, n_free=len(c["xf"]))
+    for got, key in zip(grads, ("d_xc", "d_yc", "d_h", "d_W", "d_b")):
+        got = got.cpu().numpy()
+        assert np.all(np.isfinite(got)), (mask, key)
+        assert mixed_err(got, G[key]) < tol_for(kind), (mask, kind, K, key, mixed_err(got, G[key]))

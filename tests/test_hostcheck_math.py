@@ -126,3 +126,32 @@ def test_generic_1d(hc, name, level):
     assert mixed_err(out[0], G["d_xc"]) < TOL
     assert mixed_err(out[1], G["d_h"]) < TOL
     assert mixed_err(out[2:], G["d_W"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["g2d_k1", "g2d_nofixed", "g2d_wide"])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_structured_upstream_backward(hc, name, mode):
+    """Backward specialised on which upstream gradients exist (only u_xx,u_yy / only u) gives
+    the gradients of the full formula with zeros in the absent rows."""
+    c = load_case(name)
+    if int(c["K"]) != 1:
+        pytest.skip("fast path is K=1")
+    xc, yc, h = _nodes2d(c)
+    x, y, W = f32(c["x"]), f32(c["y"]), f32(c["W"]).reshape(-1)[:xc.size]
+    N, M = x.size, xc.size
+    rs = np.random.RandomState(3)
+    g6 = np.zeros((6, N, 1))
+    if mode == 1:
+        g = f32(rs.randn(2, N))
+        g6[3, :, 0], g6[4, :, 0] = g[0], g[1]
+    else:
+        g = f32(rs.randn(1, N))
+        g6[0, :, 0] = g[0]
+    dc, dd, dh, dW = (np.zeros(M, np.float32) for _ in range(4))
+    hc.hc_g2_bwd_mode(mode, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W),
+                      _ptr(dc), _ptr(dd), _ptr(dh), _ptr(dW))
+    G = cf.grads2d("gaussian", x, y, xc, yc, h, W.reshape(1, -1), g6)
+    assert mixed_err(dc, G["d_xc"]) < TOL
+    assert mixed_err(dd, G["d_yc"]) < TOL
+    assert mixed_err(dh, G["d_h"]) < TOL
+    assert mixed_err(dW, G["d_W"][0]) < TOL

@@ -26,18 +26,23 @@ def time_ms(fn, reps=4):
     return best
 
 
+MASK = [0]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=4194304)
-    ap.add_argument("--fwd", default="0,1,2,3,4,5,6")
-    ap.add_argument("--bwd", default="0,1,2,3,4,5,6")
+    ap.add_argument("--fwd", default="0,1,2,3")
+    ap.add_argument("--bwd", default="0,1,2,3")
     ap.add_argument("--waves", default="2,4,8")
+    ap.add_argument("--mask", type=lambda v: int(v, 0), default=0)
     a = ap.parse_args()
+    MASK[0] = a.mask
     pde, nn = synthetic.make_state(samples=a.samples, device="cuda")
     xs, ys = (t.detach() for t in pde.p_samples)
     N, M = xs.numel(), nn.layer1.n
     os.environ["SPINN_TUNE"] = "fwd=0,bwd=0,waves=2"
-    step = PoissonInteriorStep(nn, xs, ys)
+    step = PoissonInteriorStep(nn, xs, ys, structured=a.mask != 0)
     ref = step.run(all_reduce=False).clone()
     ref_jets = step.jets.clone()
     lib, P = step.lib, (lambda t: None if t is None else t.data_ptr())
@@ -51,7 +56,7 @@ def main():
 
     def bwd():
         p = step.pack
-        assert lib.spinn2d_jets_bwd(0, 2, N, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y), P(l1.xf),
+        assert lib.spinn2d_jets_bwd(0, 2, MASK[0], N, step.Mf, step.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y), P(l1.xf),
                                     P(l1.yf), P(l1.h), 0, P(l2.weight), P(step.gjets), P(p.view("d_x")),
                                     P(p.view("d_y")), P(p.view("d_h")), P(p.view("d_W")), P(p.view("d_b")),
                                     P(step.ws_b), step.ws_b.numel(), S()) == 0
