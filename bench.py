@@ -32,8 +32,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "point-node evals/sec for fused residual fwd+bwd"
 UNIT = "point-node evals/s"
-FLOP_PER_PAIR = 76.0          # 23 fwd + 13 recompute + 40 bwd
-FLOP_FWD, FLOP_BWD = 23.0, 53.0
+# algorithmic flops per point-node pair (FMA = 2).  General path: SURVEY.md 8(d): 23 fwd + 53 bwd
+# (13 recompute + 40) = 76.  The benchmarked Poisson residual only has u_xx,u_yy upstream
+# gradients, so its backward runs the structured variant: 9 (geometry) + 20 = 29 flops
+# (instruction list in spinn_math.cuh:g2_bwd_pair_lapl) -> 52 per pair.
+FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 29.0
 MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
 
@@ -56,6 +59,8 @@ def parse():
     p.add_argument("--cpu-chunk", type=int, default=16384)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--general-backward", action="store_true",
+                   help="time the general 5-row backward instead of the structured (u_xx,u_yy) one")
     return p.parse_args()
 
 
@@ -221,7 +226,9 @@ def run_ours(args):
     xs, ys = xs_all[lo:hi].contiguous(), ys_all[lo:hi].contiguous()
     del xs_all, ys_all
     n_loc = hi - lo
-    step = PoissonInteriorStep(nn, xs, ys, n_total=N)
+    step = PoissonInteriorStep(nn, xs, ys, n_total=N, structured=not args.general_backward)
+    FLOP_BWD = FLOP_BWD_GENERAL if args.general_backward else FLOP_BWD_STRUCTURED
+    FLOP_PER_PAIR = FLOP_FWD + FLOP_BWD
 
     def barrier():
         if ws > 1:
@@ -399,12 +406,13 @@ def run_ours(args):
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     hbm_bytes_step = 60.0 * n_loc + 64.0 * n_loc / 2 * 2          # jets/gjets/x/y + packed point records w+r
     roofline = {
-        "bound": "fp32", "kernel": "g2k1_bwd_kernel<2>",
+        "bound": "fp32", "kernel": "g2k1_bwd_kernel (%s upstream)" % ("general 5-row" if args.general_backward else "structured u_xx,u_yy"),
         "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
         "frac": ach_bwd / measured_fp32, "traffic": None,
         "peak_source": "best in-run FMA probe (spinn_microbench: FFMA/FFMA2 chains, register operands, 64 warps/SM), lane-FMA/s x 2",
         "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
-        "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR},
+        "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR,
+                                      "bwd_general_5_rows": FLOP_BWD_GENERAL},
         "kernels": {
             "fwd": {"ms": ms_fwd, "tflops": ach_fwd / 1e12, "frac": ach_fwd / measured_fp32},
             "bwd": {"ms": ms_bwd, "tflops": ach_bwd / 1e12, "frac": ach_bwd / measured_fp32},

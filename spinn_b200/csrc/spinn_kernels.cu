@@ -431,18 +431,20 @@ __global__ void __launch_bounds__(GEN_THREADS)
 fwd_generic_kernel(int N, int Mp, const float* __restrict__ x, const float* __restrict__ y,
                    const float* __restrict__ soa, const float* __restrict__ bias,
                    float* __restrict__ jets) {
+  // thread = TWO consecutive points in the two lanes of packed f32x2 arithmetic (F2)
   constexpr int NJ = njets(DIM, LEVEL);
   constexpr int NROW = DIM + 1 + K;              // c,(d),r,W_k  (the h row is skipped)
   constexpr int TN = GEN_TILE_NODES;
   __shared__ float sm[NROW * TN];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float px = i < N ? x[i] : 0.f;
-  const float py = (DIM == 2 && i < N) ? y[i] : 0.f;
-  float acc[NJ][K];
+  const long long i0 = 2LL * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  const bool v0 = i0 < N, v1 = i0 + 1 < N;
+  const F2 px(v0 ? x[i0] : 0.f, v1 ? x[i0 + 1] : 0.f);
+  const F2 py((DIM == 2 && v0) ? y[i0] : 0.f, (DIM == 2 && v1) ? y[i0 + 1] : 0.f);
+  F2 acc[NJ][K];
 #pragma unroll
   for (int a = 0; a < NJ; ++a)
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[a][k] = 0.f;
+    for (int k = 0; k < K; ++k) acc[a][k] = F2(0.f);
 
   for (int t0 = 0; t0 < Mp; t0 += TN) {
     const int n = min(TN, Mp - t0);
@@ -453,6 +455,7 @@ fwd_generic_kernel(int N, int Mp, const float* __restrict__ x, const float* __re
       sm[row * TN + col] = soa[(size_t)srow * Mp + t0 + col];
     }
     __syncthreads();
+#pragma unroll 2
     for (int j = 0; j < n; ++j) {
       float Wk[K];
 #pragma unroll
@@ -460,20 +463,22 @@ fwd_generic_kernel(int N, int Mp, const float* __restrict__ x, const float* __re
       if (DIM == 2)
         generic_fwd_pair<DIM, KIND, K, LEVEL>(px - sm[j], py - sm[TN + j], sm[2 * TN + j], Wk, acc);
       else
-        generic_fwd_pair<DIM, KIND, K, LEVEL>(px - sm[j], 0.f, sm[TN + j], Wk, acc);
+        generic_fwd_pair<DIM, KIND, K, LEVEL>(px - sm[j], F2(0.f), sm[TN + j], Wk, acc);
     }
   }
-  if (i < N) {
 #pragma unroll
-    for (int a = 0; a < NJ; ++a)
+  for (int a = 0; a < NJ; ++a)
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        jets[((size_t)a * N + i) * K + k] = acc[a][k] + ((a == 0 && bias) ? bias[k] : 0.f);
-  }
+    for (int k = 0; k < K; ++k) {
+      const float b = (a == 0 && bias) ? bias[k] : 0.f;
+      if (v0) jets[((size_t)a * N + i0) * K + k] = acc[a][k].v.x + b;
+      if (v1) jets[((size_t)a * N + i0 + 1) * K + k] = acc[a][k].v.y + b;
+    }
 }
 
 // -----------------------------------------------------------------------------
-// GENERIC backward: thread = one node, points tiled through shared memory.
+// GENERIC backward: thread = one node, points tiled through shared memory, two
+// points per step in the lanes of packed arithmetic.
 // partial rows: 0 dc, (1 dd), DIM dh, DIM+1+k dW_k.
 // -----------------------------------------------------------------------------
 template <int DIM, int KIND, int K, int LEVEL>
@@ -482,9 +487,11 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
                    const float* __restrict__ y, const float* __restrict__ gj, int mask,
                    const float* __restrict__ soa, float* __restrict__ partials) {
   constexpr int NG = njets(DIM, LEVEL);
-  constexpr int TP = GEN_TILE_POINTS;
+  constexpr int TP = GEN_TILE_POINTS;            // even
   constexpr int NACC = DIM + 1 + K;
-  __shared__ float spx[TP], spy[DIM == 2 ? TP : 1], sg[NG * K * TP];
+  __shared__ __align__(16) float spx[TP];
+  __shared__ __align__(16) float spy[DIM == 2 ? TP : 2];
+  __shared__ __align__(16) float sg[NG * K * TP];
   const int j = blockIdx.x * GEN_THREADS + threadIdx.x;     // < Mp (Mp multiple of GEN_THREADS)
   int row = 0;
   const float c = soa[(size_t)(row++) * Mp + j];
@@ -503,27 +510,32 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
   const long long i_end = min((long long)N, i_begin + pts_per_chunk);
   for (long long t0 = i_begin; t0 < i_end; t0 += TP) {
     const int n = (int)min((long long)TP, i_end - t0);
+    const int n_even = (n + 1) & ~1;
     __syncthreads();
-    for (int e = threadIdx.x; e < n; e += GEN_THREADS) {
-      spx[e] = x[t0 + e];
-      if (DIM == 2) spy[e] = y[t0 + e];
+    for (int e = threadIdx.x; e < n_even; e += GEN_THREADS) {
+      const bool v = e < n;                       // odd tail: a zero-gradient dummy point
+      spx[e] = v ? x[t0 + e] : 0.f;
+      if (DIM == 2) spy[e] = v ? y[t0 + e] : 0.f;
 #pragma unroll
       for (int a = 0; a < NG; ++a)
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          sg[(a * K + k) * TP + e] = ((mask >> a) & 1) ? gj[((size_t)a * N + t0 + e) * K + k] : 0.f;
+          sg[(a * K + k) * TP + e] = (v && ((mask >> a) & 1)) ? gj[((size_t)a * N + t0 + e) * K + k] : 0.f;
     }
     __syncthreads();
-    float acc[NACC];
+    F2 acc[NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float X = spx[i] - c;
-      const float Y = DIM == 2 ? spy[i] - dn : 0.f;
-      generic_bwd_pair<DIM, KIND, K, LEVEL>(X, Y, r, Wk, sg + i, TP, acc);
+    for (int a = 0; a < NACC; ++a) acc[a] = F2(0.f);
+    for (int i = 0; i < n_even; i += 2) {
+      const F2 X = F2(*reinterpret_cast<const float2*>(&spx[i])) - c;
+      const F2 Y = DIM == 2 ? F2(*reinterpret_cast<const float2*>(&spy[DIM == 2 ? i : 0])) - dn : F2(0.f);
+      F2 g[NG * K];
+#pragma unroll
+      for (int q = 0; q < NG * K; ++q) g[q] = F2(*reinterpret_cast<const float2*>(&sg[q * TP + i]));
+      generic_bwd_pair<DIM, KIND, K, LEVEL>(X, Y, r, Wk, g, acc);
     }
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) tot[a] += acc[a];
+    for (int a = 0; a < NACC; ++a) tot[a] += vlane_sum(acc[a]);
   }
   float* out = partials + (size_t)blockIdx.y * NACC * Mp;
 #pragma unroll
@@ -789,7 +801,7 @@ template <int DIM, int KIND, int K>
 static void launch_fwd_generic_level(int level, int N, int Mp, const float* x, const float* y,
                                      const float* soa, const float* bias, float* jets,
                                      cudaStream_t s) {
-  dim3 grid(ceil_div_i(N, GEN_THREADS)), block(GEN_THREADS);
+  dim3 grid(ceil_div_i(N, 2 * GEN_THREADS)), block(GEN_THREADS);
   switch (level) {
     case 0: fwd_generic_kernel<DIM, KIND, K, 0><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets); break;
     case 1: fwd_generic_kernel<DIM, KIND, K, 1><<<grid, block, 0, s>>>(N, Mp, x, y, soa, bias, jets); break;

@@ -313,212 +313,260 @@ SP_HD constexpr int njets(int dim, int level) {
 // d[] layout 1-D: 0:phi 1:x 2:xx 3:xxx
 // =============================================================================
 
+// ---- lane abstraction: the generic formulas are written once for T = float (one pair per
+// thread) and T = F2 (two pairs per thread in the two lanes of packed f32x2 instructions) ----
+struct F2 {
+  float2 v;
+  SP_HD F2() {}
+  SP_HD F2(float a) : v(make_float2(a, a)) {}
+  SP_HD F2(float a, float b) : v(make_float2(a, b)) {}
+  SP_HD explicit F2(float2 a) : v(a) {}
+};
+SP_HD F2 operator+(F2 a, F2 b) { return F2(f2add(a.v, b.v)); }
+SP_HD F2 operator-(F2 a) { return F2(-a.v.x, -a.v.y); }
+SP_HD F2 operator-(F2 a, F2 b) { return F2(f2add(a.v, (-b).v)); }
+SP_HD F2 operator*(F2 a, F2 b) { return F2(f2mul(a.v, b.v)); }
+SP_HD F2 operator+(F2 a, float b) { return a + F2(b); }
+SP_HD F2 operator+(float a, F2 b) { return F2(a) + b; }
+SP_HD F2 operator-(F2 a, float b) { return a + F2(-b); }
+SP_HD F2 operator-(float a, F2 b) { return F2(a) - b; }
+SP_HD F2 operator*(F2 a, float b) { return a * F2(b); }
+SP_HD F2 operator*(float a, F2 b) { return F2(a) * b; }
+SP_HD F2& operator+=(F2& a, F2 b) { a = a + b; return a; }
+SP_HD F2& operator-=(F2& a, F2 b) { a = a - b; return a; }
+
+SP_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+SP_HD F2 vfma(F2 a, F2 b, F2 c) { return F2(f2fma(a.v, b.v, c.v)); }
+SP_HD F2 vfma(float a, F2 b, F2 c) { return vfma(F2(a), b, c); }
+SP_HD F2 vfma(F2 a, float b, F2 c) { return vfma(a, F2(b), c); }
+SP_HD F2 vfma(F2 a, F2 b, float c) { return vfma(a, b, F2(c)); }
+SP_HD F2 vfma(float a, F2 b, float c) { return vfma(F2(a), b, F2(c)); }
+SP_HD F2 vfma(F2 a, float b, float c) { return vfma(a, F2(b), F2(c)); }
+SP_HD float vex2(float x) { return ex2f_fast(x); }
+SP_HD F2 vex2(F2 x) { return F2(ex2f_fast(x.v.x), ex2f_fast(x.v.y)); }
+SP_HD float vlg2(float x) { return lg2f_fast(x); }
+SP_HD F2 vlg2(F2 x) { return F2(lg2f_fast(x.v.x), lg2f_fast(x.v.y)); }
+SP_HD float vrcp(float x) { return rcpf_fast(x); }
+SP_HD F2 vrcp(F2 x) { return F2(rcpf_fast(x.v.x), rcpf_fast(x.v.y)); }
+SP_HD float vabs(float x) { return fabsf(x); }
+SP_HD F2 vabs(F2 x) { return F2(fabsf(x.v.x), fabsf(x.v.y)); }
+// x < thr ? a : b, per lane
+SP_HD float vsel_lt(float x, float thr, float a, float b) { return x < thr ? a : b; }
+SP_HD F2 vsel_lt(F2 x, float thr, F2 a, F2 b) {
+  return F2(x.v.x < thr ? a.v.x : b.v.x, x.v.y < thr ? a.v.y : b.v.y);
+}
+// copysign(m, s) for m >= 0, per lane
+SP_HD float vcopysign(float m, float s) { return copysignf(m, s); }
+SP_HD F2 vcopysign(F2 m, F2 s) { return F2(copysignf(m.v.x, s.v.x), copysignf(m.v.y, s.v.y)); }
+SP_HD float vlane_sum(float x) { return x; }
+SP_HD float vlane_sum(F2 x) { return x.v.x + x.v.y; }
+
 // log1p(w) for 0 <= w <= ~3 from s = w/(1+w):  log1p(w) = -log(1-s).
 // MUFU.LG2 has an ABSOLUTE error of ~2^-22 near 1, so small w takes the series.
-SP_HD float log1p_from_sig(float w, float s) {
+template <class T>
+SP_HD T log1p_from_sig(T w, T s) {
   // -log(1-s) = s + s^2/2 + ... ; s <= 0.2 on this branch, 9 terms -> < 1e-7 relative
-  float p = 1.0f / 9.0f;
-  p = fmaf(p, s, 1.0f / 8.0f);
-  p = fmaf(p, s, 1.0f / 7.0f);
-  p = fmaf(p, s, 1.0f / 6.0f);
-  p = fmaf(p, s, 1.0f / 5.0f);
-  p = fmaf(p, s, 1.0f / 4.0f);
-  p = fmaf(p, s, 1.0f / 3.0f);
-  p = fmaf(p, s, 1.0f / 2.0f);
-  p = fmaf(p, s, 1.0f);
-  float small = p * s;
-  float big = LN2_F * lg2f_fast(1.0f + w);
-  return (w < 0.25f) ? small : big;
+  T p = T(1.0f / 9.0f);
+  p = vfma(p, s, 1.0f / 8.0f);
+  p = vfma(p, s, 1.0f / 7.0f);
+  p = vfma(p, s, 1.0f / 6.0f);
+  p = vfma(p, s, 1.0f / 5.0f);
+  p = vfma(p, s, 1.0f / 4.0f);
+  p = vfma(p, s, 1.0f / 3.0f);
+  p = vfma(p, s, 1.0f / 2.0f);
+  p = vfma(p, s, 1.0f);
+  T small = p * s;
+  T big = LN2_F * vlg2(1.0f + w);
+  return vsel_lt(w, 0.25f, small, big);
 }
 
-// one coordinate of the hat: e = exp(-2|s|), A = 1+e
-// om = 1-e without cancellation: for v = 2|s| < 0.5 the Taylor series of 1-exp(-v) (the MUFU
-// result has a 2^-22 RELATIVE error on e ~ 1, i.e. ~1e-7 ABSOLUTE on 1-e, which would be a
-// 1e-5 relative error on tanh(s) at |s| ~ 0.01).
-struct HatAxis { float e, A, om, sgn; };
-SP_HD HatAxis hat_axis(float s) {
-  HatAxis a;
-  const float v = 2.0f * fabsf(s);
-  a.e = ex2f_fast(-LOG2E_F * v);
+// one coordinate of the hat: e = exp(-2|s|), A = 1+e, om = 1-e, th = tanh(s)*A
+// om without cancellation: for v = 2|s| < 0.5 the Taylor series of 1-exp(-v) (the MUFU result
+// has a 2^-22 RELATIVE error on e ~ 1, i.e. ~1e-7 ABSOLUTE on 1-e, which would be a 1e-5
+// relative error on tanh(s) at |s| ~ 0.01).
+template <class T>
+struct HatAxis { T e, A, som; };     // som = sign(s) * (1 - e)
+template <class T>
+SP_HD HatAxis<T> hat_axis(T s) {
+  HatAxis<T> a;
+  const T v = 2.0f * vabs(s);
+  a.e = vex2(-LOG2E_F * v);
   a.A = 1.0f + a.e;
-  float p = -1.0f / 40320.0f;
-  p = fmaf(p, v, 1.0f / 5040.0f);
-  p = fmaf(p, v, -1.0f / 720.0f);
-  p = fmaf(p, v, 1.0f / 120.0f);
-  p = fmaf(p, v, -1.0f / 24.0f);
-  p = fmaf(p, v, 1.0f / 6.0f);
-  p = fmaf(p, v, -0.5f);
-  p = fmaf(p, v, 1.0f);
-  a.om = (v < 0.5f) ? p * v : 1.0f - a.e;
-  a.sgn = (s < 0.0f) ? -1.0f : 1.0f;
+  T p = T(-1.0f / 40320.0f);
+  p = vfma(p, v, 1.0f / 5040.0f);
+  p = vfma(p, v, -1.0f / 720.0f);
+  p = vfma(p, v, 1.0f / 120.0f);
+  p = vfma(p, v, -1.0f / 24.0f);
+  p = vfma(p, v, 1.0f / 6.0f);
+  p = vfma(p, v, -0.5f);
+  p = vfma(p, v, 1.0f);
+  const T om = vsel_lt(v, 0.5f, p * v, 1.0f - a.e);
+  a.som = vcopysign(om, s);
   return a;
 }
 
-template <int KIND, int ORDER>
-SP_HD void phi_derivs_2d(float X, float Y, float r, float* d) {
+template <int KIND, int ORDER, class T>
+SP_HD void phi_derivs_2d(T X, T Y, float r, T* d) {
   const float rho = r * r;
   if (KIND == GAUSSIAN) {
-    float a = rho * X, b = rho * Y;
-    float q = fmaf(a, X, b * Y);
-    float p = ex2f_fast(-0.5f * LOG2E_F * q);
+    T a = rho * X, b = rho * Y;
+    T q = vfma(a, X, b * Y);
+    T p = vex2((-0.5f * LOG2E_F) * q);
     d[0] = p;
-    if (ORDER >= 1) { d[1] = -a * p; d[2] = -b * p; }
+    if (ORDER >= 1) { d[1] = -(a * p); d[2] = -(b * p); }
     if (ORDER >= 2) {
-      float A2 = fmaf(a, a, -rho), B2 = fmaf(b, b, -rho);
+      T A2 = vfma(a, a, -rho), B2 = vfma(b, b, -rho);
       d[3] = A2 * p; d[4] = B2 * p; d[5] = a * b * p;
       if (ORDER >= 3) {
         d[6] = a * (2.0f * rho - A2) * p;      // (3 rho a - a^3) = a (2 rho - (a^2-rho))
         d[9] = b * (2.0f * rho - B2) * p;
-        d[7] = -a * B2 * p;
-        d[8] = -A2 * b * p;
+        d[7] = -(a * B2 * p);
+        d[8] = -(A2 * b * p);
       }
     }
   } else {
-    HatAxis ax = hat_axis(X * r), ay = hat_axis(Y * r);
-    float AA = ax.A * ay.A;
-    float R = rcpf_fast(AA);
-    float w = HAT_EK2_F * (ax.e * ay.e) * (R * R);              // e^z
-    float inv1w = rcpf_fast(1.0f + w);
-    float sg = w * inv1w;                                       // sigmoid(z)
-    float S = log1p_from_sig(w, sg);
+    HatAxis<T> ax = hat_axis(X * r), ay = hat_axis(Y * r);
+    T AA = ax.A * ay.A;
+    T R = vrcp(AA);
+    T w = HAT_EK2_F * (ax.e * ay.e) * (R * R);                  // e^z
+    T inv1w = vrcp(1.0f + w);
+    T sg = w * inv1w;                                           // sigmoid(z)
+    T S = log1p_from_sig(w, sg);
     d[0] = S * HAT_IFAC_F;
     if (ORDER >= 1) {
-      float iAx = ay.A * R, iAy = ax.A * R;                     // 1/Ax, 1/Ay
-      float Tx = ax.sgn * ax.om * iAx;                  // tanh
-      float Ty = ay.sgn * ay.om * iAy;
-      float zx = -2.0f * r * Tx, zy = -2.0f * r * Ty;
-      float sgF = sg * HAT_IFAC_F;
+      T iAx = ay.A * R, iAy = ax.A * R;                         // 1/Ax, 1/Ay
+      T Tx = ax.som * iAx, Ty = ay.som * iAy;                   // tanh
+      T zx = (-2.0f * r) * Tx, zy = (-2.0f * r) * Ty;
+      T sgF = sg * HAT_IFAC_F;
       d[1] = sgF * zx; d[2] = sgF * zy;
       if (ORDER >= 2) {
-        float Cx = 4.0f * ax.e * iAx * iAx;                     // sech^2 without cancellation
-        float Cy = 4.0f * ay.e * iAy * iAy;
-        float zxx = -2.0f * rho * Cx, zyy = -2.0f * rho * Cy;
-        float s1 = sgF * inv1w;                                 // sigma (1-sigma)/F
-        d[3] = fmaf(s1 * zx, zx, sgF * zxx);
-        d[4] = fmaf(s1 * zy, zy, sgF * zyy);
+        T Cx = 4.0f * ax.e * iAx * iAx;                         // sech^2 without cancellation
+        T Cy = 4.0f * ay.e * iAy * iAy;
+        T zxx = (-2.0f * rho) * Cx, zyy = (-2.0f * rho) * Cy;
+        T s1 = sgF * inv1w;                                     // sigma (1-sigma)/F
+        d[3] = vfma(s1 * zx, zx, sgF * zxx);
+        d[4] = vfma(s1 * zy, zy, sgF * zyy);
         d[5] = s1 * zx * zy;
         if (ORDER >= 3) {
-          float s2 = s1 * (inv1w - sg);                         // sigma1 (1-2 sigma)
-          float zxxx = -2.0f * zxx * r * Tx;                    // 4 r^3 T C
-          float zyyy = -2.0f * zyy * r * Ty;
-          d[6] = fmaf(s2 * zx * zx, zx, fmaf(3.0f * s1 * zx, zxx, sgF * zxxx));
-          d[9] = fmaf(s2 * zy * zy, zy, fmaf(3.0f * s1 * zy, zyy, sgF * zyyy));
-          d[7] = zx * fmaf(s2 * zy, zy, s1 * zyy);
-          d[8] = zy * fmaf(s2 * zx, zx, s1 * zxx);
+          T s2 = s1 * (inv1w - sg);                             // sigma1 (1-2 sigma)
+          T zxxx = (-2.0f * r) * zxx * Tx;                      // 4 r^3 T C
+          T zyyy = (-2.0f * r) * zyy * Ty;
+          d[6] = vfma(s2 * zx * zx, zx, vfma(3.0f * s1 * zx, zxx, sgF * zxxx));
+          d[9] = vfma(s2 * zy * zy, zy, vfma(3.0f * s1 * zy, zyy, sgF * zyyy));
+          d[7] = zx * vfma(s2 * zy, zy, s1 * zyy);
+          d[8] = zy * vfma(s2 * zx, zx, s1 * zxx);
         }
       }
     }
   }
 }
 
-template <int KIND, int ORDER>
-SP_HD void phi_derivs_1d(float X, float r, float* d) {
+template <int KIND, int ORDER, class T>
+SP_HD void phi_derivs_1d(T X, float r, T* d) {
   const float rho = r * r;
   if (KIND == GAUSSIAN) {
-    float a = rho * X;
-    float p = ex2f_fast(-0.5f * LOG2E_F * a * X);
+    T a = rho * X;
+    T p = vex2((-0.5f * LOG2E_F) * (a * X));
     d[0] = p;
-    if (ORDER >= 1) d[1] = -a * p;
+    if (ORDER >= 1) d[1] = -(a * p);
     if (ORDER >= 2) {
-      float A2 = fmaf(a, a, -rho);
+      T A2 = vfma(a, a, -rho);
       d[2] = A2 * p;
       if (ORDER >= 3) d[3] = a * (2.0f * rho - A2) * p;
     }
   } else {
-    HatAxis ax = hat_axis(X * r);
-    float iA = rcpf_fast(ax.A);
-    float w = HAT_EK1_F * ax.e * iA * iA;
-    float inv1w = rcpf_fast(1.0f + w);
-    float sg = w * inv1w;
-    float S = log1p_from_sig(w, sg);
+    HatAxis<T> ax = hat_axis(X * r);
+    T iA = vrcp(ax.A);
+    T w = HAT_EK1_F * ax.e * iA * iA;
+    T inv1w = vrcp(1.0f + w);
+    T sg = w * inv1w;
+    T S = log1p_from_sig(w, sg);
     d[0] = S * HAT_IFAC_F;
     if (ORDER >= 1) {
-      float T = ax.sgn * ax.om * iA;
-      float zx = -2.0f * r * T;
-      float sgF = sg * HAT_IFAC_F;
+      T Th = ax.som * iA;
+      T zx = (-2.0f * r) * Th;
+      T sgF = sg * HAT_IFAC_F;
       d[1] = sgF * zx;
       if (ORDER >= 2) {
-        float C = 4.0f * ax.e * iA * iA;
-        float zxx = -2.0f * rho * C;
-        float s1 = sgF * inv1w;
-        d[2] = fmaf(s1 * zx, zx, sgF * zxx);
+        T C = 4.0f * ax.e * iA * iA;
+        T zxx = (-2.0f * rho) * C;
+        T s1 = sgF * inv1w;
+        d[2] = vfma(s1 * zx, zx, sgF * zxx);
         if (ORDER >= 3) {
-          float s2 = s1 * (inv1w - sg);
-          float zxxx = -2.0f * zxx * r * T;
-          d[3] = fmaf(s2 * zx * zx, zx, fmaf(3.0f * s1 * zx, zxx, sgF * zxxx));
+          T s2 = s1 * (inv1w - sg);
+          T zxxx = (-2.0f * r) * zxx * Th;
+          d[3] = vfma(s2 * zx * zx, zx, vfma(3.0f * s1 * zx, zxx, sgF * zxxx));
         }
       }
     }
   }
 }
 
-
 // ---- generic per-pair accumulation (shared by the kernels and tests/hostcheck) ----
-// forward: acc[a][k] += W_k * phi_a
-template <int DIM, int KIND, int K, int LEVEL>
-SP_HD void generic_fwd_pair(float X, float Y, float r, const float* Wk, float (*acc)[K]) {
+// forward: acc[a][k] += W_k * phi_a          (T = float: one pair, T = F2: two pairs)
+template <int DIM, int KIND, int K, int LEVEL, class T>
+SP_HD void generic_fwd_pair(T X, T Y, float r, const float* Wk, T (*acc)[K]) {
   constexpr int NJ = njets(DIM, LEVEL);
   constexpr int ORDER = LEVEL >= 2 ? 2 : LEVEL;
-  float d[10];
+  T d[10];
   if (DIM == 2) phi_derivs_2d<KIND, ORDER>(X, Y, r, d);
   else phi_derivs_1d<KIND, ORDER>(X, r, d);
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
-    for (int a = 0; a < NJ; ++a) acc[a][k] = fmaf(Wk[k], d[a], acc[a][k]);
+    for (int a = 0; a < NJ; ++a) acc[a][k] = vfma(Wk[k], d[a], acc[a][k]);
 }
 
-// backward: acc rows 0 dc, (1 dd), DIM dh, DIM+1+k dW_k; g[(a*K+k)*gstride] upstream grads.
+// backward: acc rows 0 dc, (1 dd), DIM dh, DIM+1+k dW_k; g[a*K+k] upstream grads (registers).
 // Kernel-agnostic: d/dc = -d/dx, and Euler scaling for d/dh.
-template <int DIM, int KIND, int K, int LEVEL>
-SP_HD void generic_bwd_pair(float X, float Y, float r, const float* Wk, const float* g, int gstride,
-                            float* acc) {
+template <int DIM, int KIND, int K, int LEVEL, class T>
+SP_HD void generic_bwd_pair(T X, T Y, float r, const float* Wk, const T* g, T* acc) {
   constexpr int NG = njets(DIM, LEVEL);
   constexpr int ORDER = (LEVEL + 1) > 3 ? 3 : (LEVEL + 1);
-  float d[10];
+  T d[10];
   if (DIM == 2) phi_derivs_2d<KIND, ORDER>(X, Y, r, d);
   else phi_derivs_1d<KIND, ORDER>(X, r, d);
-  float G[NG];
+  T G[NG];
 #pragma unroll
-  for (int a = 0; a < NG; ++a) G[a] = 0.f;
+  for (int a = 0; a < NG; ++a) G[a] = T(0.f);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    float s = 0.f;
+    T s = T(0.f);
 #pragma unroll
     for (int a = 0; a < NG; ++a) {
-      const float gv = g[(a * K + k) * gstride];
-      s = fmaf(gv, d[a], s);
-      G[a] = fmaf(Wk[k], gv, G[a]);
+      const T gv = g[a * K + k];
+      s = vfma(gv, d[a], s);
+      G[a] = vfma(Wk[k], gv, G[a]);
     }
     acc[DIM + 1 + k] += s;
   }
   if (DIM == 2) {
     // mdc, mdd hold -dc_ij, -dd_ij
-    float mdc = G[0] * d[1], mdd = G[0] * d[2], ord = 0.f;
+    T mdc = G[0] * d[1], mdd = G[0] * d[2], ord = T(0.f);
     if (NG >= 3) {
-      mdc = fmaf(G[1 % NG], d[3], fmaf(G[2 % NG], d[5], mdc));
-      mdd = fmaf(G[1 % NG], d[5], fmaf(G[2 % NG], d[4], mdd));
-      ord = fmaf(G[1 % NG], d[1], G[2 % NG] * d[2]);
+      mdc = vfma(G[1 % NG], d[3], vfma(G[2 % NG], d[5], mdc));
+      mdd = vfma(G[1 % NG], d[5], vfma(G[2 % NG], d[4], mdd));
+      ord = vfma(G[1 % NG], d[1], G[2 % NG] * d[2]);
     }
     if (NG >= 5) {
-      mdc = fmaf(G[3 % NG], d[6], fmaf(G[4 % NG], d[7], mdc));
-      mdd = fmaf(G[3 % NG], d[8], fmaf(G[4 % NG], d[9], mdd));
-      ord = fmaf(2.f * G[3 % NG], d[3], fmaf(2.f * G[4 % NG], d[4], ord));
+      mdc = vfma(G[3 % NG], d[6], vfma(G[4 % NG], d[7], mdc));
+      mdd = vfma(G[3 % NG], d[8], vfma(G[4 % NG], d[9], mdd));
+      ord = vfma(2.f * G[3 % NG], d[3], vfma(2.f * G[4 % NG], d[4], ord));
     }
     if (NG >= 6) {
-      mdc = fmaf(G[5 % NG], d[8], mdc);
-      mdd = fmaf(G[5 % NG], d[7], mdd);
-      ord = fmaf(2.f * G[5 % NG], d[5], ord);
+      mdc = vfma(G[5 % NG], d[8], mdc);
+      mdd = vfma(G[5 % NG], d[7], mdd);
+      ord = vfma(2.f * G[5 % NG], d[5], ord);
     }
     acc[0] -= mdc;
     acc[1] -= mdd;
-    acc[2] -= r * fmaf(X, mdc, fmaf(Y, mdd, ord));
+    acc[2] -= r * vfma(X, mdc, vfma(Y, mdd, ord));
   } else {
-    float mdc = G[0] * d[1], ord = 0.f;
-    if (NG >= 2) { mdc = fmaf(G[1 % NG], d[2], mdc); ord = G[1 % NG] * d[1]; }
-    if (NG >= 3) { mdc = fmaf(G[2 % NG], d[3], mdc); ord = fmaf(2.f * G[2 % NG], d[2], ord); }
+    T mdc = G[0] * d[1], ord = T(0.f);
+    if (NG >= 2) { mdc = vfma(G[1 % NG], d[2], mdc); ord = G[1 % NG] * d[1]; }
+    if (NG >= 3) { mdc = vfma(G[2 % NG], d[3], mdc); ord = vfma(2.f * G[2 % NG], d[2], ord); }
     acc[0] -= mdc;
-    acc[1] -= r * fmaf(X, mdc, ord);
+    acc[1] -= r * vfma(X, mdc, ord);
   }
 }
 

@@ -117,9 +117,54 @@ static void gen_bwd(int N, int M, const float* x, const float* y, const float* g
     for (int i = 0; i < N; ++i) {
       for (int a = 0; a < NG; ++a) for (int k = 0; k < K; ++k) gp[a * K + k] = g[((size_t)a * N + i) * K + k];
       generic_bwd_pair<DIM, KIND, K, LEVEL>(x[i] - c[j], DIM == 2 ? y[i] - d[j] : 0.f, 1.0f / h[j], Wk,
-                                            gp.data(), 1, acc);
+                                            gp.data(), acc);
     }
     for (int a = 0; a < NACC; ++a) out[(size_t)a * M + j] = acc[a];
+  }
+}
+
+template <int DIM, int KIND, int K, int LEVEL>
+static void gen_fwd2(int N, int M, const float* x, const float* y, const float* c, const float* d,
+                     const float* h, const float* W, const float* bias, float* jets) {
+  constexpr int NJ = njets(DIM, LEVEL);
+  for (int i = 0; i < N; i += 2) {
+    bool v1 = i + 1 < N;
+    F2 px(x[i], v1 ? x[i + 1] : 0.f), py(DIM == 2 ? y[i] : 0.f, (DIM == 2 && v1) ? y[i + 1] : 0.f);
+    F2 acc[NJ][K];
+    for (int a = 0; a < NJ; ++a) for (int k = 0; k < K; ++k) acc[a][k] = F2(0.f);
+    for (int j = 0; j < M; ++j) {
+      float Wk[K];
+      for (int k = 0; k < K; ++k) Wk[k] = W[(size_t)k * M + j];
+      generic_fwd_pair<DIM, KIND, K, LEVEL>(px - c[j], DIM == 2 ? py - d[j] : F2(0.f), 1.0f / h[j], Wk, acc);
+    }
+    for (int a = 0; a < NJ; ++a) for (int k = 0; k < K; ++k) {
+      float b = (a == 0 && bias) ? bias[k] : 0.f;
+      jets[((size_t)a * N + i) * K + k] = acc[a][k].v.x + b;
+      if (v1) jets[((size_t)a * N + i + 1) * K + k] = acc[a][k].v.y + b;
+    }
+  }
+}
+
+template <int DIM, int KIND, int K, int LEVEL>
+static void gen_bwd2(int N, int M, const float* x, const float* y, const float* g, const float* c,
+                     const float* d, const float* h, const float* W, float* out /*[NACC][M]*/) {
+  constexpr int NG = njets(DIM, LEVEL);
+  constexpr int NACC = DIM + 1 + K;
+  for (int j = 0; j < M; ++j) {
+    F2 acc[NACC];
+    for (int a = 0; a < NACC; ++a) acc[a] = F2(0.f);
+    float Wk[K];
+    for (int k = 0; k < K; ++k) Wk[k] = W[(size_t)k * M + j];
+    for (int i = 0; i < N; i += 2) {
+      bool v1 = i + 1 < N;
+      F2 gp[NG * K];
+      for (int a = 0; a < NG; ++a) for (int k = 0; k < K; ++k)
+        gp[a * K + k] = F2(g[((size_t)a * N + i) * K + k], v1 ? g[((size_t)a * N + i + 1) * K + k] : 0.f);
+      F2 X = F2(x[i], v1 ? x[i + 1] : 0.f) - c[j];
+      F2 Y = DIM == 2 ? F2(y[i], v1 ? y[i + 1] : 0.f) - d[j] : F2(0.f);
+      generic_bwd_pair<DIM, KIND, K, LEVEL>(X, Y, 1.0f / h[j], Wk, gp, acc);
+    }
+    for (int a = 0; a < NACC; ++a) out[(size_t)a * M + j] = vlane_sum(acc[a]);
   }
 }
 
@@ -157,6 +202,19 @@ void hc_generic_bwd(int dim, int kind, int level, int K, int N, int M, const flo
                     const float* g, const float* c, const float* d, const float* h, const float* W,
                     float* out) {
   HC_DISPATCH(gen_bwd, N, M, x, y, g, c, d, h, W, out)
+}
+
+// the same, two points per step in packed lanes (what the CUDA kernels do)
+void hc_generic_fwd2(int dim, int kind, int level, int K, int N, int M, const float* x, const float* y,
+                     const float* c, const float* d, const float* h, const float* W, const float* bias,
+                     float* jets) {
+  HC_DISPATCH(gen_fwd2, N, M, x, y, c, d, h, W, bias, jets)
+}
+
+void hc_generic_bwd2(int dim, int kind, int level, int K, int N, int M, const float* x, const float* y,
+                     const float* g, const float* c, const float* d, const float* h, const float* W,
+                     float* out) {
+  HC_DISPATCH(gen_bwd2, N, M, x, y, g, c, d, h, W, out)
 }
 
 }  // extern "C"

@@ -76,7 +76,10 @@ def test_fast_gaussian_forward_and_backward(hc, name):
 
 @pytest.mark.parametrize("name", OP_CASES_2D)
 @pytest.mark.parametrize("level", [0, 1, 2, 3])
-def test_generic_2d(hc, name, level):
+@pytest.mark.parametrize("packed", [False, True])
+def test_generic_2d(hc, name, level, packed):
+    fwd = hc.hc_generic_fwd2 if packed else hc.hc_generic_fwd
+    bwd = hc.hc_generic_bwd2 if packed else hc.hc_generic_bwd
     c = load_case(name)
     K = int(c["K"])
     kind = cf.kind_id(c["kind"])
@@ -85,13 +88,13 @@ def test_generic_2d(hc, name, level):
     N, M = x.size, xc.size
     nj = (1, 3, 5, 6)[level]
     jets = np.zeros((nj, N, K), np.float32)
-    hc.hc_generic_fwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
+    fwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
     ref = cf.jets2d(kind, x, y, xc, yc, h, W, b)
     for a in range(nj):
         assert mixed_err(jets[a], ref[a]) < TOL, (name, level, a)
     g = f32(np.random.RandomState(5).randn(nj, N, K))
     out = np.zeros((3 + K, M), np.float32)
-    hc.hc_generic_bwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(out))
+    bwd(2, kind, level, K, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), _ptr(out))
     g6 = np.zeros((6, N, K), np.float64)
     g6[:nj] = g
     G = cf.grads2d(kind, x, y, xc, yc, h, W, g6)
@@ -103,7 +106,10 @@ def test_generic_2d(hc, name, level):
 
 @pytest.mark.parametrize("name", OP_CASES_1D)
 @pytest.mark.parametrize("level", [0, 1, 2])
-def test_generic_1d(hc, name, level):
+@pytest.mark.parametrize("packed", [False, True])
+def test_generic_1d(hc, name, level, packed):
+    fwd = hc.hc_generic_fwd2 if packed else hc.hc_generic_fwd
+    bwd = hc.hc_generic_bwd2 if packed else hc.hc_generic_bwd
     c = load_case(name)
     K = int(c["K"])
     kind = cf.kind_id(c["kind"])
@@ -113,13 +119,13 @@ def test_generic_1d(hc, name, level):
     N, M = x.size, xc.size
     nj = level + 1
     jets = np.zeros((nj, N, K), np.float32)
-    hc.hc_generic_fwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(xc), None, _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
+    fwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(xc), None, _ptr(h), _ptr(W), _ptr(b), _ptr(jets))
     ref = cf.jets1d(kind, x, xc, h, W, b)
     for a in range(nj):
         assert mixed_err(jets[a], ref[a]) < TOL, (name, level, a)
     g = f32(np.random.RandomState(6).randn(nj, N, K))
     out = np.zeros((2 + K, M), np.float32)
-    hc.hc_generic_bwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(g), _ptr(xc), None, _ptr(h), _ptr(W), _ptr(out))
+    bwd(1, kind, level, K, N, M, _ptr(x), None, _ptr(g), _ptr(xc), None, _ptr(h), _ptr(W), _ptr(out))
     g3 = np.zeros((3, N, K), np.float64)
     g3[:nj] = g
     G = cf.grads1d(kind, x, xc, h, W, g3)
