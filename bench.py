@@ -427,6 +427,66 @@ def run_ours(args):
         "microbench_lane_ops_per_s": peaks,
     }
 
+    # the general 5-row backward on the same inputs (what a residual using all jets would cost)
+    general = None
+    if ws == 1 and not args.general_backward:
+        gstep = PoissonInteriorStep(nn, xs, ys, n_total=N, structured=False)
+        gstep.gjets.copy_(step.gjets)
+
+        def bwd_general():
+            p = gstep.pack
+            rc = lib.spinn2d_jets_bwd(nn.kind, 2, 0, n_loc, gstep.Mf, gstep.Mx, 1, P(xs), P(ys), P(l1.x), P(l1.y),
+                                      P(l1.xf), P(l1.yf), P(l1.h), hs, P(l2.weight), P(gstep.gjets),
+                                      P(p.view("d_x")), P(p.view("d_y")), P(p.view("d_h")), P(p.view("d_W")),
+                                      P(p.view("d_b")), P(gstep.ws_b), gstep.ws_b.numel(), S())
+            assert rc == 0
+
+        ms_g = time_call(bwd_general)
+        nloss = step.pack.slices["loss"][0]
+        diff = float((gstep.pack.flat[:nloss] - step.pack.flat[:nloss]).abs().max()
+                     / step.pack.flat[:nloss].abs().max())
+        general = {"bwd_ms": ms_g, "bwd_tflops": pairs_loc * FLOP_BWD_GENERAL / (ms_g * 1e-3) / 1e12,
+                   "step_ms_equivalent": ms_step - ms_bwd + ms_g,
+                   "evals_per_s_equivalent": N * M / ((ms_step - ms_bwd + ms_g) * 1e-3),
+                   "max_rel_diff_vs_structured": diff,
+                   "note": "same gradients; the structured variant skips terms whose upstream gradient "
+                           "(u, u_x, u_y) is structurally absent for this residual"}
+        del gstep
+
+    # the reference's dense eager algorithm on THIS GPU (oracle port on cuda), largest chunk that fits
+    gpu_eager = None
+    if ws == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import torch_port as tp
+            chunk = 65536
+            xg = xs[:chunk].clone().requires_grad_(True)
+            yg = ys[:chunk].clone().requires_grad_(True)
+            leaves = [t.detach().clone().requires_grad_(True) for t in (l1.x, l1.y, l1.h, l2.weight, l2.bias)]
+
+            def eager():
+                for t in leaves + [xg, yg]:
+                    t.grad = None
+                xc = torch.cat((leaves[0], l1.xf))
+                yc = torch.cat((leaves[1], l1.yf))
+                U = tp.forward2d(args.kind, xg, yg, xc, yc, leaves[2], leaves[3], leaves[4]).squeeze()
+                ux, uy = tp._d(U, (xg, yg))
+                uxx, _ = tp._d(ux, (xg, yg))
+                _, uyy = tp._d(uy, (xg, yg))
+                f = 20 * np.pi ** 2 * torch.sin(2 * np.pi * xg) * torch.sin(4 * np.pi * yg)
+                ((0.1 * (uxx + uyy + f)) ** 2).sum().div(N).backward()
+
+            eager()
+            ms_eager = time_call(eager, reps=3)
+            gpu_eager = {"value": chunk * M / (ms_eager * 1e-3), "unit": UNIT, "ms_per_chunk": ms_eager,
+                         "points_per_chunk": chunk,
+                         "what": "oracle/torch_port.py dense (N,M) eager + 3x autograd.grad + backward on the "
+                                 "same B200 (the reference's --gpu algorithm; it cannot hold more than "
+                                 "~400K points x 4096 nodes at ~100 B/pair)"}
+            del xg, yg, leaves
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            gpu_eager = {"error": repr(exc)[:200]}
+
     cpu_baseline = None
     if ws == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=3, warmup=1)
@@ -449,7 +509,8 @@ def run_ours(args):
                                  if ws > 1 else "none (1 GPU)"},
         "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
         "clocks": clocks, "e2e": e2e, "gpu_launches": PoissonInteriorStep.LAUNCHES * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "general_upstream": general,
+        "reference_algorithm_on_this_gpu": gpu_eager,
     }
     print(json.dumps(line), flush=True)
     if ws > 1:
