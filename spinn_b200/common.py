@@ -171,6 +171,9 @@ class Optimizer:
         if getattr(args, "graph", False) and cls is Optimizer:
             from .graphed import GraphedOptimizer
             cls = GraphedOptimizer
+        elif cls is Optimizer and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            from .dist_optimizer import DistributedOptimizer      # one process per GPU (torchrun)
+            cls = DistributedOptimizer
         return cls(pde, nn, plotter, n_train=args.n_train, n_skip=args.n_skip, tol=args.tol,
                    lr=args.lr, plot=args.plot, out_dir=args.directory, opt_class=opt_class)
 
@@ -274,7 +277,10 @@ class App:
 
     def run(self, args=None, **kw):
         args = self.setup_argparse(**kw).parse_args(args)
-        device("cuda" if args.gpu else "cpu")
+        if args.gpu and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")   # torchrun: one GPU per process
+        else:
+            device("cuda" if args.gpu else "cpu")
         activation = self._get_activation(args)
         self.pde = self.pde_cls.from_args(args)
         self.nn = self.nn_cls.from_args(self.pde, activation, args).to(device())

@@ -85,3 +85,66 @@ class GradPack:
 
     def nbytes(self):
         return self.flat.numel() * 4
+
+
+# --------------------------------------------------------------------------------------
+# Data-parallel training through the plug-in surface (any problem class, any config)
+# --------------------------------------------------------------------------------------
+def shard_interior(pde, rank=None, world_size=None):
+    """Make `pde.interior()` return this rank's contiguous slice of the interior points.
+
+    Works for problem classes that keep their interior samples in `p_samples`
+    (RegularPDE / IBVP2D / CavityPDE), `interior_samples` (irregular-domain Poisson2D) or
+    `xs` (BasicODE).  Every rank keeps ALL boundary points; shards must be equal-sized (checked)
+    so that the mean over ranks of local means is the global mean.  DistributedOptimizer combines
+    the two loss terms accordingly.  Random sub-sampling (`sample_frac<1`) draws from the local
+    slice with the local RNG stream."""
+    if rank is None:
+        rank, world_size, _ = world()
+    if world_size == 1:
+        return pde
+    for attr in ("p_samples", "interior_samples", "xs"):
+        if hasattr(pde, attr):
+            break
+    else:
+        raise TypeError("do not know where this problem class keeps its interior samples")
+    pts = getattr(pde, attr)
+    single = torch.is_tensor(pts)
+    tensors = (pts,) if single else tuple(pts)
+    n = tensors[0].numel()
+    if n % world_size != 0:
+        raise ValueError(f"{n} interior points do not split evenly over {world_size} ranks")
+    lo, hi = shard_range(n, rank, world_size)
+    local = tuple(t.detach()[lo:hi].clone().requires_grad_(t.requires_grad) for t in tensors)
+    setattr(pde, attr, local[0] if single else local)
+    if hasattr(pde, "rng_interior"):
+        import numpy as np
+        pde.n_interior_local = hi - lo
+        pde.rng_interior = np.arange(hi - lo)
+        pde.sample_size = int(pde.sample_frac * (hi - lo))
+    pde._shard = (rank, world_size, lo, hi)
+    return pde
+
+
+def all_reduce_gradients(params, average=True, buf=None):
+    """ONE collective for all parameter gradients: pack -> all_reduce -> unpack."""
+    params = [p for p in params if p.grad is not None]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not params:
+        return buf
+    n = sum(p.grad.numel() for p in params)
+    if buf is None or buf.numel() != n or buf.device != params[0].grad.device:
+        buf = torch.empty(n, dtype=params[0].grad.dtype, device=params[0].grad.device)
+    off = 0
+    for p in params:
+        k = p.grad.numel()
+        buf[off:off + k].copy_(p.grad.reshape(-1))
+        off += k
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    if average:
+        buf.div_(dist.get_world_size())
+    off = 0
+    for p in params:
+        k = p.grad.numel()
+        p.grad.copy_(buf[off:off + k].reshape(p.grad.shape))
+        off += k
+    return buf

@@ -16,6 +16,7 @@ from .pde2d_base import RegularPDE, _grid, _side
 
 class CavityPDE(RegularPDE):
     NU = 0.01
+    interior_reduction = "sum"     # interior_loss is a SUM over points (cavity.py:96-100)
 
     def __init__(self, n_nodes, ns, nb=None, nbs=None, sample_frac=1.0):
         self.sample_frac = sample_frac

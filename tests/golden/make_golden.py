@@ -259,10 +259,35 @@ def main():
                 "--activation", "softplus"])
     trajectory("irreg", "poisson2d_irreg_dom", from_mod("Poisson2D", "App2D", "SPINN2D", "PointCloud"),
                ["--n-train", "60", "--lr", "1e-3"])
+    # two more callers on the same surface (space-time problems on IBVP2D, code/ibvp2d_base.py)
+    trajectory("heat1d", "heat1d", from_mod("Heat1D", "App2D", "SPINN2D", "HeatPlotter"),
+               ["--nodes", "50", "--samples", "200", "--lr", "1e-2", "--n-train", "60"])
+    trajectory("burgers1d", "burgers1d", from_mod("Burgers1D", "App2D", "SPINN2D", "MyPlotter"),
+               ["--nodes", "40", "--samples", "200", "--lr", "1e-3", "--n-train", "60"])
     trajectory("cavity", "cavity", from_mod("CavityPDE", "App2D", "SPINN2D", "CavityPlotter"),
                ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4",
                 "--n-train", "100"])
 
 
+def only(names):
+    """Regenerate a subset:  python tests/golden/make_golden.py traj:heat1d traj:burgers1d"""
+    load_reference()
+    from_mod = lambda cls_name, app_name, nn_name, pl_name: (
+        lambda m: getattr(m, app_name)(pde_cls=getattr(m, cls_name), nn_cls=getattr(m, nn_name),
+                                       plotter_cls=getattr(m, pl_name)))
+    table = {
+        "traj:heat1d": lambda: trajectory("heat1d", "heat1d", from_mod("Heat1D", "App2D", "SPINN2D", "HeatPlotter"),
+                                          ["--nodes", "50", "--samples", "200", "--lr", "1e-2", "--n-train", "60"]),
+        "traj:burgers1d": lambda: trajectory("burgers1d", "burgers1d",
+                                             from_mod("Burgers1D", "App2D", "SPINN2D", "MyPlotter"),
+                                             ["--nodes", "40", "--samples", "200", "--lr", "1e-3", "--n-train", "60"]),
+    }
+    for n in names:
+        table[n]()
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        only(sys.argv[1:])
+    else:
+        main()

@@ -91,7 +91,8 @@ def _traj(name):
 @pytest.mark.parametrize("name,modname", [
     ("ode3", "ode3"), ("ode3_softplus", "ode3"),
     ("poisson2d_sine", "poisson2d_sine"), ("poisson2d_sine_softplus", "poisson2d_sine"),
-    ("irreg", "poisson2d_irreg_dom"), ("cavity", "cavity")])
+    ("irreg", "poisson2d_irreg_dom"), ("cavity", "cavity"),
+    ("heat1d", "heat1d"), ("burgers1d", "burgers1d")])
 def test_config_trajectory_on_gpu_matches_reference(name, modname):
     import importlib
     mod = importlib.import_module(f"spinn_b200.problems.{modname}")

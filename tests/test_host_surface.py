@@ -11,7 +11,7 @@ import torch
 from helpers import GOLDEN, OracleBackend, load_case, maxnorm_err
 from oracle import torch_port as tp
 from spinn_b200 import common, ops, spinn1d, spinn2d
-from spinn_b200.problems import cavity, derivs, ode3, poisson2d_irreg_dom, poisson2d_sine
+from spinn_b200.problems import burgers1d, cavity, derivs, heat1d, ode3, poisson2d_irreg_dom, poisson2d_sine
 
 
 @pytest.fixture()
@@ -171,7 +171,8 @@ def _traj(name):
 @pytest.mark.parametrize("name,mod,steps", [
     ("ode3", ode3, 300), ("ode3_softplus", ode3, 120),
     ("poisson2d_sine", poisson2d_sine, 60), ("poisson2d_sine_softplus", poisson2d_sine, 30),
-    ("irreg", poisson2d_irreg_dom, 8), ("cavity", cavity, 40)])
+    ("irreg", poisson2d_irreg_dom, 8), ("cavity", cavity, 40),
+    ("heat1d", heat1d, 40), ("burgers1d", burgers1d, 40)])
 def test_config_loss_trajectory_matches_reference(oracle_backend, name, mod, steps, capsys):
     ref, args = _traj(name)
     i = args.index("--n-train")
@@ -201,7 +202,7 @@ sys.path.insert(0, "%(root)s"); sys.path.insert(0, os.path.join("%(root)s", "tes
 from helpers import OracleBackend
 from spinn_b200 import ops
 ops.set_backend(OracleBackend())
-import poisson2d_sine, cavity, ode3                # UNCHANGED reference files
+import poisson2d_sine, cavity, ode3, heat1d, burgers1d   # UNCHANGED reference files
 import spinn2d, common
 assert spinn2d.__file__.startswith("%(root)s") and common.__file__.startswith("%(root)s")
 out = {}
@@ -211,7 +212,11 @@ for name, mod, cls, appn, nn_name, pl, args in [
     ("cavity", cavity, "CavityPDE", "App2D", "SPINN2D", "CavityPlotter",
      ["--nodes","100","--samples","2500","--sample-frac","0.1","--lr","5e-4","--n-train","15"]),
     ("ode3", ode3, "ODESimple", "App1D", "SPINN1D", "Plotter1D",
-     ["--nodes","3","--samples","60","--n-train","50","--lr","1e-3","--tol","1e-3"])]:
+     ["--nodes","3","--samples","60","--n-train","50","--lr","1e-3","--tol","1e-3"]),
+    ("heat1d", heat1d, "Heat1D", "App2D", "SPINN2D", "HeatPlotter",
+     ["--nodes","50","--samples","200","--lr","1e-2","--n-train","20"]),
+    ("burgers1d", burgers1d, "Burgers1D", "App2D", "SPINN2D", "MyPlotter",
+     ["--nodes","40","--samples","200","--lr","1e-3","--n-train","20"])]:
     np.random.seed(0); torch.manual_seed(0)
     app = getattr(mod, appn)(pde_cls=getattr(mod, cls), nn_cls=getattr(mod, nn_name), plotter_cls=getattr(mod, pl))
     app.run(args=args)
@@ -223,8 +228,59 @@ np.savez(sys.argv[1], **out)
         f = os.path.join(td, "out.npz")
         subprocess.check_call([sys.executable, "-c", code, f], stdout=subprocess.DEVNULL)
         got = np.load(f)
-        for name in ("poisson2d_sine", "cavity", "ode3"):
+        for name in ("poisson2d_sine", "cavity", "ode3", "heat1d", "burgers1d"):
             ref, _ = _traj(name)
             n = len(got[name])
             rel = np.abs(got[name] - ref[:n]) / np.abs(ref[:n])
             assert rel.max() < 1e-4, (name, rel.max())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_problem_mirrors_generate_the_reference_point_sets():
+    """spinn_b200.problems.* rebuild nodes / samples / boundary points bit-for-bit as the
+    reference classes do (RegularPDE, CavityPDE, BasicODE, IBVP2D, irregular-domain Poisson2D)."""
+    import subprocess
+    code = r'''
+import sys, types, os
+import numpy as np, torch
+for n in ("matplotlib", "matplotlib.pyplot", "mayavi", "mayavi.mlab"):
+    sys.modules[n] = types.ModuleType(n)
+sys.path.insert(0, "%(ref)s"); sys.path.insert(0, "%(root)s")
+import pde2d_base as R2, ode_base as R1, ibvp2d_base as RI, cavity as RC, poisson2d_irreg_dom as RP
+from spinn_b200.problems import pde2d_base as M2, ode_base as M1, ibvp2d_base as MI, cavity as MC
+from spinn_b200.problems import poisson2d_irreg_dom as MP
+def same(a, b):
+    a = [np.asarray(t.detach().cpu() if torch.is_tensor(t) else t, dtype=np.float64) for t in a]
+    b = [np.asarray(t.detach().cpu() if torch.is_tensor(t) else t, dtype=np.float64) for t in b]
+    assert len(a) == len(b)
+    for u, v in zip(a, b):
+        assert u.shape == v.shape and np.array_equal(u, v), (u.shape, v.shape)
+for args in [(100, 400), (25, 100, 7, 9), (3600, 4096, 124)]:
+    r, m = R2.RegularPDE(*args), M2.RegularPDE(*args)
+    for f in ("nodes", "fixed_nodes", "interior", "boundary", "plot_points"):
+        same(getattr(r, f)(), getattr(m, f)())
+for args in [(100, 2500, None, None, 0.1), (49, 400, 0, 11, 1.0)]:
+    r, m = RC.CavityPDE(*args), MC.CavityPDE(*args)
+    for f in ("nodes", "fixed_nodes", "boundary", "plot_points"):
+        same(getattr(r, f)(), getattr(m, f)())
+    same(r.p_samples, m.p_samples)
+    np.random.seed(1); a = r.interior(); np.random.seed(1); b = m.interior(); same(a, b)
+for args in [(3, 60), (10, 30)]:
+    r, m = R1.BasicODE(*args), M1.BasicODE(*args)
+    same([r.nodes()], [m.nodes()]); same([r.fixed_nodes()], [m.fixed_nodes()])
+    same([r.interior()], [m.interior()]); same([r.boundary()], [m.boundary()]); same([r.plot_points()], [m.plot_points()])
+for args in [(50, 200), (40, 200, 5, 30, -1.0, 2.0, 0.5), (30, 100, 0, None, 0.0, 1.0, 1.0)]:
+    r, m = RI.IBVP2D(*args), MI.IBVP2D(*args)
+    for f in ("nodes", "fixed_nodes", "interior", "boundary", "plot_points"):
+        same(getattr(r, f)(), getattr(m, f)())
+d = os.path.join("%(ref)s", "mesh_data")
+files = [os.path.join(d, f + ".dat") for f in ("interior_nodes", "boundary_nodes", "interior_samples", "boundary_samples")]
+r = RP.Poisson2D(*files)
+m = MP.Poisson2D("npz:interior_nodes", "npz:boundary_nodes", "npz:interior_samples", "npz:boundary_samples")
+m2 = MP.Poisson2D(*files)
+for f in ("nodes", "fixed_nodes", "interior", "boundary", "plot_points"):
+    same(getattr(r, f)(), getattr(m, f)()); same(getattr(r, f)(), getattr(m2, f)())
+print("ok")
+''' % {"ref": REF, "root": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
