@@ -242,3 +242,36 @@ class _Attach1(torch.autograd.Function):
         if gx.dim() > 1:
             gx = gx.sum(-1)
         return g, gx, None
+
+
+# --------------------------------------------------------------------------------------
+# partition of unity: jets of u = T/S from the jets of T = sum W phi and S = sum phi
+# --------------------------------------------------------------------------------------
+def quotient_jets_2d(T, S):
+    """T: list of (N, K) jets of the weighted sum, S: list of (N, 1) jets of the plain sum, in
+    the order u, ux, uy[, uxx, uyy[, uxy]].  Returns the jets of u = T/S (quotient rule)."""
+    inv = 1.0 / S[0]
+    u = T[0] * inv
+    out = [u]
+    if len(T) >= 3:
+        ux = (T[1] - u * S[1]) * inv
+        uy = (T[2] - u * S[2]) * inv
+        out += [ux, uy]
+    if len(T) >= 5:
+        out.append((T[3] - 2.0 * ux * S[1] - u * S[3]) * inv)
+        out.append((T[4] - 2.0 * uy * S[2] - u * S[4]) * inv)
+    if len(T) >= 6:
+        out.append((T[5] - ux * S[2] - uy * S[1] - u * S[5]) * inv)
+    return tuple(out)
+
+
+def quotient_jets_1d(T, S):
+    inv = 1.0 / S[0]
+    u = T[0] * inv
+    out = [u]
+    if len(T) >= 2:
+        ux = (T[1] - u * S[1]) * inv
+        out.append(ux)
+    if len(T) >= 3:
+        out.append((T[2] - 2.0 * ux * S[1] - u * S[2]) * inv)
+    return tuple(out)

@@ -83,11 +83,11 @@ class SPINN1D(nn.Module):
 
     def __init__(self, pde, activation, fixed_h=False, use_pu=False):
         super().__init__()
-        if use_pu:
-            raise NotImplementedError("--pu (partition of unity) is not on the fused B200 path yet")
         self.fixed_h, self.use_pu = fixed_h, use_pu
         self.activation = activation
         self.kind = kernel_kind(activation)
+        if pde.n_vars() + int(use_pu) > ops.MAX_K:
+            raise NotImplementedError(f"n_vars={pde.n_vars()} (+1 with --pu) > {ops.MAX_K} not supported")
         self.layer1 = Shift(pde.nodes(), pde.fixed_nodes(), fixed_h=fixed_h)
         self.layer2 = nn.Linear(self.layer1.n, pde.n_vars(), bias=not use_pu)
         self.layer2.weight.data.fill_(0.0)
@@ -96,8 +96,15 @@ class SPINN1D(nn.Module):
 
     def jets(self, x, level=2):
         l1, l2 = self.layer1, self.layer2
-        return ops.fused_jets(1, self.kind, level, x.detach().contiguous(), None,
-                              l1.center, None, l1.fixed, None, l1.h, l2.weight, l2.bias)
+        if not self.use_pu:
+            return ops.fused_jets(1, self.kind, level, x.detach().contiguous(), None,
+                                  l1.center, None, l1.fixed, None, l1.h, l2.weight, l2.bias)
+        # partition of unity (reference spinn1d.py:151-155): extra all-ones output row, then the
+        # quotient rule on the jets (see spinn2d.SPINN2D.jets)
+        W = torch.cat((l2.weight, torch.ones_like(l2.weight[:1])), 0)
+        J = ops.fused_jets(1, self.kind, level, x.detach().contiguous(), None,
+                           l1.center, None, l1.fixed, None, l1.h, W, None)
+        return ops.quotient_jets_1d([j[:, :-1] for j in J], [j[:, -1:] for j in J])
 
     def forward(self, x):
         x = x.reshape(-1)

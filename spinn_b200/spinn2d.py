@@ -110,8 +110,6 @@ class SPINN2D(nn.Module):
 
     def __init__(self, pde, activation, fixed_h=False, use_pu=False):
         super().__init__()
-        if use_pu:
-            raise NotImplementedError("--pu (partition of unity) is not on the fused B200 path yet")
         self.activation = activation
         self.kind = kernel_kind(activation)
         self.use_pu = use_pu
@@ -120,15 +118,24 @@ class SPINN2D(nn.Module):
         self.layer2.weight.data.fill_(0.0)
         if self.layer2.bias is not None:
             self.layer2.bias.data.fill_(0.0)
-        if pde.n_vars() > ops.MAX_K:
-            raise NotImplementedError(f"n_vars={pde.n_vars()} > {ops.MAX_K} not supported")
+        if pde.n_vars() + int(use_pu) > ops.MAX_K:
+            raise NotImplementedError(f"n_vars={pde.n_vars()} (+1 with --pu) > {ops.MAX_K} not supported")
 
     # -- fused evaluation ------------------------------------------------------
     def jets(self, x, y, level=2):
         """Raw fused call: tuple of (N, K) tensors u, ux, uy, uxx, uyy[, uxy]."""
         l1, l2 = self.layer1, self.layer2
-        return ops.fused_jets(2, self.kind, level, x.detach().contiguous(), y.detach().contiguous(),
-                              l1.x, l1.y, l1.xf, l1.yf, l1.h, l2.weight, l2.bias)
+        if not self.use_pu:
+            return ops.fused_jets(2, self.kind, level, x.detach().contiguous(), y.detach().contiguous(),
+                                  l1.x, l1.y, l1.xf, l1.yf, l1.h, l2.weight, l2.bias)
+        # partition of unity (reference spinn2d.py:174-178): u = sum_j W_j phi_j / sum_j phi_j.
+        # One fused call with an extra all-ones output row gives T_a = sum W phi_a and
+        # S_a = sum phi_a; the quotient rule on the jets is O(N) differentiable torch code, so
+        # autograd carries the upstream gradients back to the same fused backward.
+        W = torch.cat((l2.weight, torch.ones_like(l2.weight[:1])), 0)
+        J = ops.fused_jets(2, self.kind, level, x.detach().contiguous(), y.detach().contiguous(),
+                           l1.x, l1.y, l1.xf, l1.yf, l1.h, W, None)
+        return ops.quotient_jets_2d([j[:, :-1] for j in J], [j[:, -1:] for j in J])
 
     def forward(self, x, y):
         x = x.reshape(-1)

@@ -87,7 +87,7 @@ def _perturb(nn, gen, dim):
             l1.center.add_(0.01 * torch.randn(l1.center.shape, generator=gen))
 
 
-def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=1.0):
+def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=1.0, use_pu=False):
     import spinn2d
     import pde2d_base
     gen = torch.Generator().manual_seed(seed)
@@ -109,7 +109,7 @@ def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=
     out = {"kind": kind, "K": K, "dim": 2}
     for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
         act = spinn2d.gaussian if kind == "gaussian" else spinn2d.SoftPlus()
-        nn = spinn2d.SPINN2D(StubPDE((xn, yn), fixed, K), act, fixed_h=fixed_h)
+        nn = spinn2d.SPINN2D(StubPDE((xn, yn), fixed, K), act, fixed_h=fixed_h, use_pu=use_pu)
         _perturb(nn, torch.Generator().manual_seed(seed + 1), 2)
         if tag == "f32":
             out.update(
@@ -117,7 +117,8 @@ def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=
                 xf=nn.layer1.x.detach().numpy().copy(), yf=nn.layer1.y.detach().numpy().copy(),
                 xfix=nn.layer1.xf.numpy().copy(), yfix=nn.layer1.yf.numpy().copy(),
                 h=nn.layer1.h.detach().numpy().reshape(-1).copy(),
-                W=nn.layer2.weight.detach().numpy().copy(), b=nn.layer2.bias.detach().numpy().copy(),
+                W=nn.layer2.weight.detach().numpy().copy(),
+                b=(np.zeros(K, np.float32) if use_pu else nn.layer2.bias.detach().numpy().copy()),
             )
         else:
             nn = _to_double(nn, act)
@@ -134,16 +135,19 @@ def op_case_2d(name, kind, n_side, nb, npts, K, seed, fixed_h=False, lo=0.0, hi=
             jets.append(torch.stack((u_, ux, uy, uxx, uyy, uxy)))
         J = torch.stack(jets, -1)                                   # (6, N, K)
         L = (torch.tensor(gj, dtype=dt) * J).sum()
-        params = [nn.layer1.x, nn.layer1.y, nn.layer1.h, nn.layer2.weight, nn.layer2.bias]
+        params = [nn.layer1.x, nn.layer1.y, nn.layer1.h, nn.layer2.weight]
+        if not use_pu:
+            params.append(nn.layer2.bias)
         gr = ag.grad(L, params)
         out["jets_" + tag] = J.detach().numpy()
         for nme, gv in zip(("d_xc", "d_yc", "d_h", "d_W", "d_b"), gr):
             out[nme + "_" + tag] = gv.numpy().reshape(-1) if nme == "d_h" else gv.numpy()
-    np.savez_compressed(os.path.join(HERE, f"op_{name}.npz"), **out)
+    out["use_pu"] = use_pu
+    np.savez_compressed(os.path.join(HERE, f"{'pu' if use_pu else 'op'}_{name}.npz"), **out)
     print("wrote", name)
 
 
-def op_case_1d(name, kind, n, npts, K, seed, fixed=True):
+def op_case_1d(name, kind, n, npts, K, seed, fixed=True, use_pu=False):
     import spinn1d
     import ode_base
     rs = np.random.RandomState(seed)
@@ -154,13 +158,14 @@ def op_case_1d(name, kind, n, npts, K, seed, fixed=True):
     out = {"kind": kind, "K": K, "dim": 1}
     for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
         act = spinn1d.gaussian if kind == "gaussian" else spinn1d.SoftPlus()
-        nn = spinn1d.SPINN1D(StubPDE(xn, fx, K), act)
+        nn = spinn1d.SPINN1D(StubPDE(xn, fx, K), act, use_pu=use_pu)
         _perturb(nn, torch.Generator().manual_seed(seed + 1), 1)
         if tag == "f32":
             out.update(
                 x=xs, gjets=gj, xf=nn.layer1.center.detach().numpy().copy(),
                 xfix=nn.layer1.fixed.numpy().copy(), h=nn.layer1.h.detach().numpy().copy(),
-                W=nn.layer2.weight.detach().numpy().copy(), b=nn.layer2.bias.detach().numpy().copy(),
+                W=nn.layer2.weight.detach().numpy().copy(),
+                b=(np.zeros(K, np.float32) if use_pu else nn.layer2.bias.detach().numpy().copy()),
             )
         else:
             nn = _to_double(nn, act)
@@ -176,12 +181,15 @@ def op_case_1d(name, kind, n, npts, K, seed, fixed=True):
             jets.append(torch.stack((u_, ux, uxx)))
         J = torch.stack(jets, -1)
         L = (torch.tensor(gj, dtype=dt) * J).sum()
-        params = [nn.layer1.center, nn.layer1.h, nn.layer2.weight, nn.layer2.bias]
+        params = [nn.layer1.center, nn.layer1.h, nn.layer2.weight]
+        if not use_pu:
+            params.append(nn.layer2.bias)
         gr = ag.grad(L, params)
         out["jets_" + tag] = J.detach().numpy()
         for nme, gv in zip(("d_xc", "d_h", "d_W", "d_b"), gr):
             out[nme + "_" + tag] = gv.numpy()
-    np.savez_compressed(os.path.join(HERE, f"op_{name}.npz"), **out)
+    out["use_pu"] = use_pu
+    np.savez_compressed(os.path.join(HERE, f"{'pu' if use_pu else 'op'}_{name}.npz"), **out)
     print("wrote", name)
 
 
@@ -267,6 +275,7 @@ def main():
     trajectory("cavity", "cavity", from_mod("CavityPDE", "App2D", "SPINN2D", "CavityPlotter"),
                ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4",
                 "--n-train", "100"])
+    only(["pu", "traj:ode3_lbfgs", "traj:sine_pu", "traj:sine_fixed_h"])
 
 
 def only(names):
@@ -282,6 +291,21 @@ def only(names):
                                              from_mod("Burgers1D", "App2D", "SPINN2D", "MyPlotter"),
                                              ["--nodes", "40", "--samples", "200", "--lr", "1e-3", "--n-train", "60"]),
     }
+    table["pu"] = lambda: (op_case_2d("g2d_k1", "gaussian", 4, 3, 61, 1, 31, use_pu=True),
+                           op_case_2d("s2d_k1", "softplus", 4, 3, 61, 1, 32, use_pu=True),
+                           op_case_2d("g2d_k3", "gaussian", 3, 4, 50, 3, 33, use_pu=True),
+                           op_case_1d("g1d_k1", "gaussian", 7, 45, 1, 34, use_pu=True),
+                           op_case_1d("s1d_k1", "softplus", 7, 45, 1, 35, use_pu=True))
+    table["traj:ode3_lbfgs"] = lambda: trajectory(
+        "ode3_lbfgs", "ode3", from_mod("ODESimple", "App1D", "SPINN1D", "Plotter1D"),
+        ["--nodes", "3", "--samples", "60", "--n-train", "6", "--lr", "1e-2", "--tol", "1e-30",
+         "--optimizer", "LBFGS"])
+    table["traj:sine_pu"] = lambda: trajectory(
+        "poisson2d_sine_pu", "poisson2d_sine", from_mod("Poisson2D", "App2D", "SPINN2D", "Plotter2D"),
+        ["--nodes", "100", "--samples", "400", "--n-train", "60", "--lr", "1e-3", "--tol", "1e-30", "--pu"])
+    table["traj:sine_fixed_h"] = lambda: trajectory(
+        "poisson2d_sine_fixed_h", "poisson2d_sine", from_mod("Poisson2D", "App2D", "SPINN2D", "Plotter2D"),
+        ["--nodes", "100", "--samples", "400", "--n-train", "60", "--lr", "1e-3", "--tol", "1e-30", "--fixed-h"])
     for n in names:
         table[n]()
 
