@@ -135,3 +135,40 @@ def test_cuda_graphed_step_follows_the_eager_trajectory(name, modname, steps):
     rel = np.abs(loss - ref[:steps]) / np.abs(ref[:steps])
     assert rel[:10].max() < 5e-5, (name, rel[:10].max())
     assert rel.max() < 3e-3, (name, rel.max())
+
+
+@pytest.mark.parametrize("name", ["g2d_k1", "s2d_k1", "g2d_k3"])
+def test_partition_of_unity_on_gpu_matches_reference(on_gpu, name):
+    """--pu: u = sum W phi / sum phi through one fused call with an extra all-ones output and the
+    quotient rule on the jets; jets and gradients vs the reference's autograd (fp64 fixtures)."""
+    from spinn_b200 import spinn2d
+    from spinn_b200.common import tensor
+    from spinn_b200.problems import derivs
+    d = np.load(os.path.join(GOLDEN, f"pu_{name}.npz"))
+    c = {k: (d[k].item() if d[k].ndim == 0 else d[k]) for k in d.files}
+    K = int(c["K"])
+    act = spinn2d.gaussian if c["kind"] == "gaussian" else spinn2d.SoftPlus()
+    nn = spinn2d.SPINN2D(_StubPDE((c["xf"], c["yf"]), (c["xfix"], c["yfix"]), K), act, use_pu=True).to("cuda")
+    with torch.no_grad():
+        nn.layer1.x.copy_(tensor(c["xf"]))
+        nn.layer1.y.copy_(tensor(c["yf"]))
+        nn.layer1.h.copy_(tensor(c["h"]))
+        nn.layer2.weight.copy_(tensor(c["W"]))
+    x = tensor(c["x"], requires_grad=True)
+    y = tensor(c["y"], requires_grad=True)
+    U = nn(x, y).reshape(x.numel(), K)
+    g = tensor(c["gjets"])
+    L = 0.0
+    for k in range(K):
+        got = torch.stack(derivs.jets_2d(U[:, k], x, y))
+        for a in range(5):
+            e_new = mixed_err(got[a].detach().cpu().numpy(), c["jets_f64"][a, :, k])
+            e_ref = mixed_err(c["jets_f32"][a, :, k], c["jets_f64"][a, :, k])
+            assert e_new < 4e-5 and e_new < 3 * e_ref + 1e-5, (name, a, e_new, e_ref)
+        L = L + (g[:5, :, k] * got).sum()
+    L.backward()
+    for got, key in [(nn.layer1.x.grad, "d_xc"), (nn.layer1.y.grad, "d_yc"), (nn.layer1.h.grad, "d_h"),
+                     (nn.layer2.weight.grad, "d_W")]:
+        e_new = mixed_err(got.cpu().numpy(), c[key + "_f64"])
+        e_ref = mixed_err(c[key + "_f32"], c[key + "_f64"])
+        assert e_new < 5e-5 and e_new < 3 * e_ref + 1e-5, (name, key, e_new, e_ref)
