@@ -508,7 +508,7 @@ def run_ours(args):
                    "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
                                  if ws > 1 else "none (1 GPU)"},
         "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": PoissonInteriorStep.LAUNCHES * args.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (PoissonInteriorStep.LAUNCHES + int(args.general_backward)) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "general_upstream": general,
         "reference_algorithm_on_this_gpu": gpu_eager,
     }

@@ -158,7 +158,7 @@ def poisson_interior_step(kind, x, y, xc, yc, h, W, b, n_total):
 # nn.Module form of the same dense algorithm (same parameter names as the
 # reference: layer1.x/.y/.h, layer2.weight/.bias; 1-D layer1.center), so that the
 # problem classes / Optimizer of spinn_b200 can drive the REFERENCE ALGORITHM on
-# any device.  Used by tests and by tools/train_step_bench.py as the "reference
+# any device.  Used by tests and by tests/perf/train_step_bench.py as the "reference
 # eager path on the same GPU" (SURVEY.md section 6).  Follows code/spinn2d.py:97-188
 # and code/spinn1d.py:88-171.
 # --------------------------------------------------------------------------- #

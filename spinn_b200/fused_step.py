@@ -21,8 +21,9 @@ UNIT_SOURCE = dict(scale=1.0, amp=0.0, kx=0.0, ky=0.0, f0=1.0)
 
 class PoissonInteriorStep:
     #: kernels of ours enqueued by one run(): pack_nodes(fwd), fwd, residual, add_partials,
-    #: pack_nodes(bwd), pack_points, bwd, bias_partial, finalize
-    LAUNCHES = 9
+    #: pack_nodes(bwd), pack_points, bwd, finalize  (+ bias_partial when u itself has an upstream
+    #: gradient, i.e. structured=False)
+    LAUNCHES = 8
 
     def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True):
         if nn.layer2.weight.shape[0] != 1:

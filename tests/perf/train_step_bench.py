@@ -3,7 +3,9 @@
 the fused B200 path vs the reference's dense eager algorithm on the SAME GPU
 (oracle/torch_port.py:DenseSPINN*, driven by the same problem classes and Optimizer).
 
-    python tools/train_step_bench.py [--steps 200]
+    python tests/perf/train_step_bench.py [--steps 200]
+
+(lives under tests/ because it times the oracle's dense modules as the comparison baseline)
 """
 import argparse
 import contextlib
@@ -16,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import torch_port  # noqa: E402
 from spinn_b200 import common  # noqa: E402
 from spinn_b200.problems import cavity, ode3, poisson2d_irreg_dom, poisson2d_sine  # noqa: E402
