@@ -115,6 +115,36 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
                              size_t workspace_bytes, void* stream);
 size_t spinn2d_poisson_residual_workspace_bytes(int N);
 
+/* ---- compact-support ("cut-off") evaluation, 2-D Gaussian kernel, K = 1  (OPT-IN; SURVEY 8f-4,
+ * manuscript :1089-1095).  Same per-pair formulas as the dense calls, but (32-node block) x
+ * (64-point group) combinations whose bounding boxes are farther apart than cutoff * h_max are
+ * skipped, so results differ from the dense ones only by the Gaussian tail beyond `cutoff`
+ * widths (relative size exp(-cutoff^2/2)).  node_perm: int32[M] visiting order of the nodes
+ * (spatially sorted, e.g. Morton; NULL = given order) -- it affects speed only, gradients come
+ * back in the caller's node order.  Consecutive points should be spatially close (grids are).
+ * stats: optional device counter; receives the number of point-node pairs actually evaluated
+ * (the dense count is N*M) so that skipped work can be reported as skipped.  The forward keeps
+ * all node records in shared memory (M up to ~4500); larger M returns SPINN_E_UNSUPPORTED. */
+size_t spinn2d_sparse_fwd_workspace_bytes(int N, int M);
+size_t spinn2d_sparse_bwd_workspace_bytes(int N, int M);
+int spinn2d_jets_fwd_sparse(int kind, int level, int N, int M_free, int M_fixed, int K,
+                            const float* x, const float* y,
+                            const float* xc_free, const float* yc_free,
+                            const float* xc_fixed, const float* yc_fixed,
+                            const float* h, int h_is_scalar, const float* W, const float* bias,
+                            const int* node_perm, float cutoff, float* jets,
+                            unsigned long long* stats, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int spinn2d_jets_bwd_sparse(int kind, int level, int present_mask, int N, int M_free, int M_fixed, int K,
+                            const float* x, const float* y,
+                            const float* xc_free, const float* yc_free,
+                            const float* xc_fixed, const float* yc_fixed,
+                            const float* h, int h_is_scalar, const float* W, const float* gjets,
+                            const int* node_perm, float cutoff,
+                            float* d_xc, float* d_yc, float* d_h, float* d_W, float* d_bias,
+                            unsigned long long* stats, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* ---- instruction-throughput probes used to measure the roofline denominators on the box
  * (spinn_b200/csrc/microbench.cu).  Every thread runs 8 independent float2 accumulator chains
  * for `iters` iterations with operands held in registers loaded from `in` (>= 64 floats), so

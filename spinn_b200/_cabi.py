@@ -29,6 +29,12 @@ SIGNATURES = {
     "spinn1d_jets_fwd": (_c_int, [_c_int] * 6 + [_c_fp] * 4 + [_c_int] + [_c_fp] * 4 + [_c_size, _c_fp]),
     "spinn1d_bwd_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
     "spinn1d_jets_bwd": (_c_int, [_c_int] * 7 + [_c_fp] * 4 + [_c_int] + [_c_fp] * 7 + [_c_size, _c_fp]),
+    "spinn2d_sparse_fwd_workspace_bytes": (_c_size, [_c_int, _c_int]),
+    "spinn2d_sparse_bwd_workspace_bytes": (_c_size, [_c_int, _c_int]),
+    "spinn2d_jets_fwd_sparse": (_c_int, [_c_int] * 6 + [_c_fp] * 7 + [_c_int] + [_c_fp] * 3 + [ctypes.c_float]
+                                + [_c_fp] * 3 + [_c_size, _c_fp]),
+    "spinn2d_jets_bwd_sparse": (_c_int, [_c_int] * 7 + [_c_fp] * 7 + [_c_int] + [_c_fp] * 3 + [ctypes.c_float]
+                                + [_c_fp] * 7 + [_c_size, _c_fp]),
     "spinn2d_poisson_residual_workspace_bytes": (_c_size, [_c_int]),
     "spinn2d_poisson_residual": (_c_int, [_c_int, ctypes.c_double] + [_c_fp] * 3 + [ctypes.c_float] * 5
                                  + [_c_fp] * 3 + [_c_size, _c_fp]),

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libspinn_b200.so")
-SOURCES = ["spinn_kernels.cu", "microbench.cu"]
-HEADERS = ["spinn_math.cuh", os.path.join("..", "..", "include", "spinn_b200.h")]
+SOURCES = ["spinn_kernels.cu", "spinn_sparse.cu", "microbench.cu"]
+HEADERS = ["spinn_math.cuh", "spinn_host.h", os.path.join("..", "..", "include", "spinn_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "../../include/spinn_b200.h"
+#include "spinn_host.h"
 #include "spinn_math.cuh"
 
 using namespace spinn;
@@ -41,6 +42,9 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+// shared with spinn_sparse.cu (spinn_host.h)
+int spinn_fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
 
 #define CUDA_TRY(expr)                                                              \
   do {                                                                              \
@@ -68,6 +72,8 @@ static int sm_count() {
   }
   return cached[dev];
 }
+
+int spinn_sm_count() { return sm_count(); }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int round_up_i(int v, int a) { return (v + a - 1) / a * a; }

@@ -25,7 +25,7 @@ class PoissonInteriorStep:
     #: gradient, i.e. structured=False)
     LAUNCHES = 8
 
-    def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True):
+    def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True, cutoff=None):
         if nn.layer2.weight.shape[0] != 1:
             raise ValueError("PoissonInteriorStep is for scalar problems (K=1)")
         self.lib = _cabi.load()
@@ -48,6 +48,14 @@ class PoissonInteriorStep:
         self.ws_f = torch.empty(self.lib.spinn2d_fwd_workspace_bytes(self.N, M, 1), dtype=torch.uint8, device=dev)
         self.ws_b = torch.empty(self.lib.spinn2d_bwd_workspace_bytes(self.N, M, 1), dtype=torch.uint8, device=dev)
         self.ws_r = torch.empty(self.lib.spinn2d_poisson_residual_workspace_bytes(self.N), dtype=torch.uint8, device=dev)
+        # compact-support mode (opt-in): Morton order of the nodes, pair counter for reporting
+        self.cutoff = float(cutoff) if cutoff else None
+        if self.cutoff:
+            from .ops import morton_order
+            self.perm = morton_order(*l1.centers())
+            self.stats = torch.zeros(2, dtype=torch.int64, device=dev)     # [fwd pairs, bwd pairs]
+            self.ws_sf = torch.empty(self.lib.spinn2d_sparse_fwd_workspace_bytes(self.N, M), dtype=torch.uint8, device=dev)
+            self.ws_sb = torch.empty(self.lib.spinn2d_sparse_bwd_workspace_bytes(self.N, M), dtype=torch.uint8, device=dev)
 
     def run(self, all_reduce=True):
         """Enqueue one interior fwd+bwd on the current stream.  Afterwards
@@ -58,6 +66,8 @@ class PoissonInteriorStep:
         hs = int(l1.h.numel() == 1)
         p = self.pack
         p.view("loss").zero_()
+        if self.cutoff:
+            return self._run_sparse(all_reduce)
         rc = lib.spinn2d_jets_fwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
                                   _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
                                   _ptr(l2.weight), _ptr(l2.bias), _ptr(self.jets), _ptr(self.ws_f),
@@ -75,6 +85,34 @@ class PoissonInteriorStep:
                                   _ptr(p.view("d_b")) if p.has("d_b") else None,
                                   _ptr(self.ws_b), self.ws_b.numel(), s)
         _cabi.check(rc, "spinn2d_jets_bwd")
+        if all_reduce:
+            p.all_reduce()
+        return p.flat
+
+    def _run_sparse(self, all_reduce):
+        lib, nn, p, s = self.lib, self.nn, self.pack, _stream()
+        l1, l2 = nn.layer1, nn.layer2
+        hs = int(l1.h.numel() == 1)
+        st = self.stats
+        rc = lib.spinn2d_jets_fwd_sparse(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
+                                         _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
+                                         _ptr(l2.weight), _ptr(l2.bias), _ptr(self.perm), self.cutoff,
+                                         _ptr(self.jets), st[0:1].data_ptr(), _ptr(self.ws_sf),
+                                         self.ws_sf.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_fwd_sparse")
+        r = self.res
+        rc = lib.spinn2d_poisson_residual(self.N, self.n_total, _ptr(self.x), _ptr(self.y), _ptr(self.jets),
+                                          r["scale"], r["amp"], r["kx"], r["ky"], r["f0"], _ptr(self.gjets),
+                                          _ptr(p.view("loss")), _ptr(self.ws_r), self.ws_r.numel(), s)
+        _cabi.check(rc, "spinn2d_poisson_residual")
+        rc = lib.spinn2d_jets_bwd_sparse(nn.kind, 2, self.upstream_mask, self.N, self.Mf, self.Mx, 1,
+                                         _ptr(self.x), _ptr(self.y), _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf),
+                                         _ptr(l1.yf), _ptr(l1.h), hs, _ptr(l2.weight), _ptr(self.gjets),
+                                         _ptr(self.perm), self.cutoff, _ptr(p.view("d_x")), _ptr(p.view("d_y")),
+                                         _ptr(p.view("d_h")), _ptr(p.view("d_W")),
+                                         _ptr(p.view("d_b")) if p.has("d_b") else None, st[1:2].data_ptr(),
+                                         _ptr(self.ws_sb), self.ws_sb.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_bwd_sparse")
         if all_reduce:
             p.all_reduce()
         return p.flat

@@ -121,6 +121,48 @@ class CudaBackend:
         return d_xc, d_yc, d_h, d_W, d_b
 
 
+    # ---- compact-support variants (2-D Gaussian, K=1); see include/spinn_b200.h -------------
+    def forward_sparse(self, level, x, y, xf, yf, xfix, yfix, h, W, b, perm, cutoff, stats=None):
+        lib = _cabi.load()
+        dev = self._check(x, y, xf, yf, xfix, yfix, h, W, b)
+        N, Mf, Mx = x.numel(), xf.numel(), xfix.numel()
+        nj = num_jets(2, level)
+        with torch.cuda.device(dev):
+            jets = torch.empty((nj, N, 1), dtype=torch.float32, device=dev)
+            if N == 0:
+                return jets
+            nbytes = lib.spinn2d_sparse_fwd_workspace_bytes(N, Mf + Mx)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = lib.spinn2d_jets_fwd_sparse(GAUSSIAN, level, N, Mf, Mx, 1, _ptr(x), _ptr(y), _ptr(xf), _ptr(yf),
+                                             _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1), _ptr(W),
+                                             _ptr(b), _ptr(perm), float(cutoff), _ptr(jets), _ptr(stats),
+                                             _ptr(ws), nbytes, _stream())
+        _cabi.check(rc, "spinn2d_jets_fwd_sparse")
+        return jets
+
+    def backward_sparse(self, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias, mask, perm, cutoff,
+                        stats=None):
+        lib = _cabi.load()
+        dev = self._check(x, y, xf, yf, xfix, yfix, h, W, gj)
+        N, Mf, Mx = x.numel(), xf.numel(), xfix.numel()
+        M = Mf + Mx
+        with torch.cuda.device(dev):
+            d_xc = torch.empty(Mf, dtype=torch.float32, device=dev)
+            d_yc = torch.empty(Mf, dtype=torch.float32, device=dev)
+            d_h = torch.empty(h.numel(), dtype=torch.float32, device=dev)
+            d_W = torch.empty((1, M), dtype=torch.float32, device=dev)
+            d_b = torch.empty(1, dtype=torch.float32, device=dev) if want_bias else None
+            nbytes = lib.spinn2d_sparse_bwd_workspace_bytes(N, M)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = lib.spinn2d_jets_bwd_sparse(GAUSSIAN, level, mask, N, Mf, Mx, 1, _ptr(x), _ptr(y), _ptr(xf),
+                                             _ptr(yf), _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1),
+                                             _ptr(W), _ptr(gj), _ptr(perm), float(cutoff), _ptr(d_xc),
+                                             _ptr(d_yc), _ptr(d_h), _ptr(d_W), _ptr(d_b), _ptr(stats),
+                                             _ptr(ws), nbytes, _stream())
+        _cabi.check(rc, "spinn2d_jets_bwd_sparse")
+        return d_xc, d_yc, d_h, d_W, d_b
+
+
 _BACKEND = CudaBackend()
 
 
@@ -149,9 +191,14 @@ class _FusedJets(torch.autograd.Function):
     spatial derivatives ARE the outputs; the tower below wires them to autograd."""
 
     @staticmethod
-    def forward(ctx, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
+    def forward(ctx, dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b, cutoff=None, perm=None):
         hk = h.reshape(-1)
-        jets = _BACKEND.forward(dim, kind, level, x, y, xf, yf, xfix, yfix, hk, W, b)
+        sparse = bool(cutoff) and sparse_supported(dim, kind, level, W.shape[0])
+        if sparse:
+            jets = _BACKEND.forward_sparse(level, x, y, xf, yf, xfix, yfix, hk, W, b, perm, cutoff)
+        else:
+            jets = _BACKEND.forward(dim, kind, level, x, y, xf, yf, xfix, yfix, hk, W, b)
+        ctx.sparse = (float(cutoff), perm) if sparse else None
         ctx.meta = (dim, kind, level)
         ctx.h_shape = h.shape
         ctx.has_bias = b is not None
@@ -166,7 +213,7 @@ class _FusedJets(torch.autograd.Function):
         x, y, xf, yf, xfix, yfix, h, W = ctx.saved_tensors
         present = [i for i, g in enumerate(gs) if g is not None]
         if not present:
-            return (None,) * 12
+            return (None,) * 14
         lv = _level_for(dim, present[-1])
         ng = num_jets(dim, lv)
         N, K = x.numel(), W.shape[0]
@@ -176,15 +223,49 @@ class _FusedJets(torch.autograd.Function):
         for i in present:
             gj[i].copy_(gs[i].reshape(N, K))
             mask |= 1 << i
-        d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward(
-            dim, kind, lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias, mask)
+        if ctx.sparse is not None and lv <= 2:
+            cutoff, perm = ctx.sparse
+            d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward_sparse(
+                lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias, mask, perm, cutoff)
+        else:
+            d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward(
+                dim, kind, lv, x, y, xf, yf, xfix, yfix, h.reshape(-1), W, gj, ctx.has_bias, mask)
         return (None, None, None, None, None, d_xc, d_yc, None, None,
-                d_h.reshape(ctx.h_shape), d_W, d_b)
+                d_h.reshape(ctx.h_shape), d_W, d_b, None, None)
 
 
-def fused_jets(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b):
-    """Tuple of jets, each (N, K).  2-D order u,ux,uy,uxx,uyy[,uxy]; 1-D u,ux,uxx."""
-    return _FusedJets.apply(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b)
+def fused_jets(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b, cutoff=None, perm=None):
+    """Tuple of jets, each (N, K).  2-D order u,ux,uy,uxx,uyy[,uxy]; 1-D u,ux,uxx.
+    cutoff (in node widths) selects the compact-support kernels where they exist (2-D Gaussian,
+    K=1, levels 2-3); perm is the int32 node visiting order for them (see morton_order)."""
+    return _FusedJets.apply(dim, kind, level, x, y, xf, yf, xfix, yfix, h, W, b, cutoff, perm)
+
+
+def sparse_supported(dim, kind, level, K):
+    return dim == 2 and kind == GAUSSIAN and K == 1 and level in (2, 3)
+
+
+def _spread_bits16(v):
+    """0000abcd -> 0a0b0c0d for 16-bit integers held in int64 tensors."""
+    v = (v | (v << 8)) & 0x00FF00FF
+    v = (v | (v << 4)) & 0x0F0F0F0F
+    v = (v | (v << 2)) & 0x33333333
+    v = (v | (v << 1)) & 0x55555555
+    return v
+
+
+def morton_order(xc, yc):
+    """int32 permutation that visits the nodes along a Z-order curve of their centres, so that
+    32 consecutive nodes form a compact block (no host synchronisation)."""
+    x = xc.detach().float()
+    y = yc.detach().float()
+    lo_x, lo_y = x.min(), y.min()
+    sx = 65535.0 / (x.max() - lo_x).clamp_min(1e-30)
+    sy = 65535.0 / (y.max() - lo_y).clamp_min(1e-30)
+    qx = ((x - lo_x) * sx).long().clamp_(0, 65535)
+    qy = ((y - lo_y) * sy).long().clamp_(0, 65535)
+    code = _spread_bits16(qx) | (_spread_bits16(qy) << 1)
+    return torch.argsort(code).to(torch.int32)
 
 
 class _Attach(torch.autograd.Function):

@@ -95,21 +95,30 @@ class SPINN2D(nn.Module):
     FLAGS = (
         (("--fixed-h",), "fixed_h", False, None, "Use fixed width nodes."),
         (("--pu",), "pu", False, None, "Use a partition of unity."),
+        # not in the reference: compact-support evaluation (Gaussian kernel, n_vars=1)
+        (("--cutoff",), "cutoff", 0.0, float,
+         "Skip node blocks farther than CUTOFF widths from a group of points (0 = dense)."),
     )
+    #: refresh the Morton visiting order of the nodes every this many fused calls (it only
+    #: affects how much is skipped, never the result)
+    perm_refresh = 64
     #: also produce u_xy so that ``ag.grad(u_x, (x, y))`` is complete (the reference
     #: computes it and drops it, pde2d_base.py:52-62); costs ~2 of 16 FP32 ops per pair
     mixed_derivative = True
 
     @classmethod
     def from_args(cls, pde, activation, args):
-        return cls(pde, activation, fixed_h=args.fixed_h, use_pu=args.pu)
+        return cls(pde, activation, fixed_h=args.fixed_h, use_pu=args.pu,
+                   cutoff=getattr(args, "cutoff", 0.0))
 
     @classmethod
     def setup_argparse(cls, parser, **kw):
         add_flags(parser, cls.FLAGS, {})
 
-    def __init__(self, pde, activation, fixed_h=False, use_pu=False):
+    def __init__(self, pde, activation, fixed_h=False, use_pu=False, cutoff=0.0):
         super().__init__()
+        self.cutoff = float(cutoff) if cutoff else None
+        self._perm, self._perm_age = None, 0
         self.activation = activation
         self.kind = kernel_kind(activation)
         self.use_pu = use_pu
@@ -126,8 +135,10 @@ class SPINN2D(nn.Module):
         """Raw fused call: tuple of (N, K) tensors u, ux, uy, uxx, uyy[, uxy]."""
         l1, l2 = self.layer1, self.layer2
         if not self.use_pu:
+            cutoff = self.cutoff if ops.sparse_supported(2, self.kind, level, l2.weight.shape[0]) else None
             return ops.fused_jets(2, self.kind, level, x.detach().contiguous(), y.detach().contiguous(),
-                                  l1.x, l1.y, l1.xf, l1.yf, l1.h, l2.weight, l2.bias)
+                                  l1.x, l1.y, l1.xf, l1.yf, l1.h, l2.weight, l2.bias,
+                                  cutoff, self.node_order() if cutoff else None)
         # partition of unity (reference spinn2d.py:174-178): u = sum_j W_j phi_j / sum_j phi_j.
         # One fused call with an extra all-ones output row gives T_a = sum W phi_a and
         # S_a = sum phi_a; the quotient rule on the jets is O(N) differentiable torch code, so
@@ -136,6 +147,14 @@ class SPINN2D(nn.Module):
         J = ops.fused_jets(2, self.kind, level, x.detach().contiguous(), y.detach().contiguous(),
                            l1.x, l1.y, l1.xf, l1.yf, l1.h, W, None)
         return ops.quotient_jets_2d([j[:, :-1] for j in J], [j[:, -1:] for j in J])
+
+    def node_order(self):
+        """Cached Morton visiting order of the nodes for the compact-support kernels."""
+        if self._perm is None or self._perm_age >= self.perm_refresh or self._perm.device != self.layer1.h.device:
+            xc, yc = self.layer1.centers()
+            self._perm, self._perm_age = ops.morton_order(xc, yc), 0
+        self._perm_age += 1
+        return self._perm
 
     def forward(self, x, y):
         x = x.reshape(-1)

@@ -88,3 +88,14 @@ class OracleBackend:
         t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32, device=x.device)
         return (t(G["d_xc"]), t(G["d_yc"]) if dim == 2 else None, t(G["d_h"]), t(G["d_W"]),
                 t(G["d_b"]) if want_bias else None)
+
+
+    def forward_sparse(self, level, x, y, xf, yf, xfix, yfix, h, W, b, perm, cutoff, stats=None):
+        assert perm is not None and sorted(perm.tolist()) == list(range(xf.numel() + xfix.numel()))
+        self.calls["forward_sparse"] = self.calls.get("forward_sparse", 0) + 1
+        return self.forward(2, 0, level, x, y, xf, yf, xfix, yfix, h, W, b)
+
+    def backward_sparse(self, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias, mask, perm, cutoff,
+                        stats=None):
+        self.calls["backward_sparse"] = self.calls.get("backward_sparse", 0) + 1
+        return self.backward(2, 0, level, x, y, xf, yf, xfix, yfix, h, W, gj, want_bias, mask)

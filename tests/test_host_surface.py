@@ -374,3 +374,20 @@ def test_result_files_have_the_reference_layout(oracle_backend, tmp_path):
     assert sorted(res.files) == ["u", "u_exact", "x", "y"] and res["u"].shape == res["x"].shape == (14, 14)
     sd = torch.load(os.path.join(d, "model.pt"))
     assert list(sd) == ["layer1.x", "layer1.y", "layer1.h", "layer2.weight", "layer2.bias"]
+
+
+def test_cutoff_flag_routes_to_the_compact_support_entry_points(oracle_backend):
+    """--cutoff: SPINN2D hands a Morton permutation of the nodes and the cut-off to the sparse
+    entry points (forward AND backward); unsupported variants silently stay dense-exact."""
+    loss = _run(poisson2d_sine.make_app(), ["--nodes", "100", "--samples", "400", "--n-train", "3",
+                                            "--lr", "1e-3", "--cutoff", "7"])
+    ref, _ = _traj("poisson2d_sine")
+    assert np.abs(loss - ref[:3]).max() / np.abs(ref[:3]).max() < 1e-5    # oracle stand-in is dense
+    assert oracle_backend.calls.get("forward_sparse", 0) >= 3 and oracle_backend.calls.get("backward_sparse", 0) >= 3
+    from spinn_b200 import ops as _ops
+    perm = _ops.morton_order(torch.rand(1000), torch.rand(1000))
+    assert perm.dtype == torch.int32 and sorted(perm.tolist()) == list(range(1000))
+    xy = torch.stack(torch.meshgrid(torch.arange(8.), torch.arange(8.), indexing="ij")).reshape(2, -1)
+    p = _ops.morton_order(xy[0], xy[1]).long()
+    blocks = xy[:, p].reshape(2, 4, 16)            # 16 consecutive nodes of an 8x8 grid = a 4x4 cell
+    assert float((blocks.max(-1).values - blocks.min(-1).values).max()) == 3.0
