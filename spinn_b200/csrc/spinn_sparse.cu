@@ -25,6 +25,7 @@ using namespace spinn;
 namespace {
 
 constexpr int NB_PAIRS = 16;          // node pairs per block (32 nodes) -- forward culling unit
+constexpr int SUP = 8;                // node blocks per super block (first culling level)
 constexpr int SUB_PAIRS = 32;         // point pairs per sub-tile (64 points) -- backward culling unit
 constexpr int FWD_T = 256;            // forward CTA
 constexpr int BWD_T = 128;            // backward CTA: 4 warps x 64 nodes
@@ -127,11 +128,28 @@ g2k1_fwd_sparse_kernel(int N, const float* __restrict__ x, const float* __restri
                        float* __restrict__ jets, int vec_ok, unsigned long long* __restrict__ stats) {
   constexpr int P = 2, NJ = MIXED ? 6 : 5, WPC = FWD_T / 32;
   extern __shared__ float4 sm4[];
+  const int nsup = (nblk + SUP - 1) / SUP;
   float4* srec = sm4;                                   // 3 * NB_PAIRS * nblk
   float4* sbb = sm4 + 3 * NB_PAIRS * nblk;              // nblk
-  float* sr2 = reinterpret_cast<float*>(sbb + nblk);    // nblk
+  float4* ssbb = sbb + nblk;                            // nsup
+  float* sr2 = reinterpret_cast<float*>(ssbb + nsup);   // nblk
+  float* ssr2 = sr2 + nblk;                             // nsup
   for (int e = threadIdx.x; e < 3 * NB_PAIRS * nblk; e += FWD_T) srec[e] = recs[e];
   for (int e = threadIdx.x; e < nblk; e += FWD_T) { sbb[e] = bb[e]; sr2[e] = reach2[e]; }
+  __syncthreads();
+  // super-block table: union box of the member blocks and the largest reach among them
+  // (conservative: dist(tile, union) <= dist(tile, member))
+  for (int e = threadIdx.x; e < nsup; e += FWD_T) {
+    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f, r2 = -1.f;
+    for (int b = e * SUP; b < min(nblk, (e + 1) * SUP); ++b) {
+      if (sr2[b] < 0.f) continue;
+      const float4 q = sbb[b];
+      xmin = fminf(xmin, q.x); xmax = fmaxf(xmax, q.y); ymin = fminf(ymin, q.z); ymax = fmaxf(ymax, q.w);
+      r2 = fmaxf(r2, sr2[b]);
+    }
+    ssbb[e] = make_float4(xmin, xmax, ymin, ymax);
+    ssr2[e] = r2;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, lw = threadIdx.x >> 5;
@@ -163,18 +181,24 @@ g2k1_fwd_sparse_kernel(int N, const float* __restrict__ x, const float* __restri
 #pragma unroll
       for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
     }
-    for (int b = 0; b < nblk; ++b) {
-      const float4 q4 = sbb[b];
-      if (box_dist2(txmin, txmax, tymin, tymax, q4.x, q4.y, q4.z, q4.w) > sr2[b]) continue;
-      const float4* r = srec + 3 * NB_PAIRS * b;
-      evaluated += 1;
+    for (int sb = 0; sb < nsup; ++sb) {
+      // level 1: a super block = SUP consecutive node blocks (256 Morton-ordered nodes)
+      const float4 s4 = ssbb[sb];
+      if (box_dist2(txmin, txmax, tymin, tymax, s4.x, s4.y, s4.z, s4.w) > ssr2[sb]) continue;
+      const int b_end = min(nblk, (sb + 1) * SUP);
+      for (int b = sb * SUP; b < b_end; ++b) {
+        const float4 q4 = sbb[b];
+        if (box_dist2(txmin, txmax, tymin, tymax, q4.x, q4.y, q4.z, q4.w) > sr2[b]) continue;
+        const float4* r = srec + 3 * NB_PAIRS * b;
+        evaluated += 1;
 #pragma unroll 4
-      for (int p = 0; p < NB_PAIRS; ++p) {
-        const float4 A = r[3 * p + 0], B = r[3 * p + 1], C = r[3 * p + 2];
-        const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
-        const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
+        for (int p = 0; p < NB_PAIRS; ++p) {
+          const float4 A = r[3 * p + 0], B = r[3 * p + 1], C = r[3 * p + 2];
+          const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
+          const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
 #pragma unroll
-        for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+          for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+        }
       }
     }
 #pragma unroll
@@ -274,30 +298,52 @@ g2k1_bwd_sparse_kernel(int N2, int nsub, int sub_per_chunk, const float4* __rest
     for (int a = 0; a < NACC; ++a) tot[q][a] = 0.f;
   unsigned long long evaluated = 0;
 
+  // warp-private staging buffer: the records of one sub-tile (32 point pairs)
+  __shared__ float4 stage[BWD_T / 32][NREC * SUB_PAIRS];
+  float4* my = stage[threadIdx.x >> 5];
   const int s_begin = blockIdx.y * sub_per_chunk;
   const int s_end = min(nsub, s_begin + sub_per_chunk);
-  for (int s = s_begin; s < s_end; ++s) {
-    const float4 q4 = __ldg(&sub_bb[s]);
-    if (box_dist2(bxmin, bxmax, bymin, bymax, q4.x, q4.y, q4.z, q4.w) > reach2) continue;
-    const int p0 = s * SUB_PAIRS, p1 = min(N2, p0 + SUB_PAIRS);
-    evaluated += (unsigned long long)(p1 - p0);
+  auto next_kept = [&](int s) {
+    for (; s < s_end; ++s) {
+      const float4 q4 = __ldg(&sub_bb[s]);
+      if (box_dist2(bxmin, bxmax, bymin, bymax, q4.x, q4.y, q4.z, q4.w) <= reach2) break;
+    }
+    return s;
+  };
+  // lane l carries pair l of the sub-tile being fetched (NREC float4, contiguous per pair)
+  float4 pre[NREC];
+  auto fetch = [&](int s) {
+    const int p = min(N2 - 1, s * SUB_PAIRS + lane);
+#pragma unroll
+    for (int k = 0; k < NREC; ++k) pre[k] = __ldg(&ptrecs[(size_t)NREC * p + k]);
+  };
+  int s = next_kept(s_begin);
+  if (s < s_end) fetch(s);
+  while (s < s_end) {
+#pragma unroll
+    for (int k = 0; k < NREC; ++k) my[NREC * lane + k] = pre[k];
+    __syncwarp();
+    const int n = min(SUB_PAIRS, N2 - s * SUB_PAIRS);
+    const int s2 = next_kept(s + 1);
+    if (s2 < s_end) fetch(s2);                     // in flight while this sub-tile is computed
+    evaluated += (unsigned long long)n;
     float2 acc[Q][NACC];
 #pragma unroll
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) acc[q][a] = f2(0.f, 0.f);
 #pragma unroll 2
-    for (int p = p0; p < p1; ++p) {
-      const float4 A = __ldg(&ptrecs[(size_t)NREC * p + 0]), B = __ldg(&ptrecs[(size_t)NREC * p + 1]);
+    for (int p = 0; p < n; ++p) {
+      const float4 A = my[NREC * p + 0], B = my[NREC * p + 1];
       const float2 x2 = f2(A.x, A.y), y2 = f2(A.z, A.w);
       if (MODE == BWD_ALL) {
-        const float4 C = __ldg(&ptrecs[(size_t)NREC * p + 2 % NREC]), D = __ldg(&ptrecs[(size_t)NREC * p + 3 % NREC]);
+        const float4 C = my[NREC * p + 2 % NREC], D = my[NREC * p + 3 % NREC];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
           g2_bwd_pair(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), f2(C.z, C.w), f2(D.x, D.y), nc[q],
                       nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q], acc[q]);
       } else if (MODE == BWD_LAPL) {
-        const float4 C = __ldg(&ptrecs[(size_t)NREC * p + 2 % NREC]);
+        const float4 C = my[NREC * p + 2 % NREC];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
           g2_bwd_pair_lapl(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), nc[q], nd[q], rp[q], acc[q]);
@@ -310,6 +356,8 @@ g2k1_bwd_sparse_kernel(int N2, int nsub, int sub_per_chunk, const float4* __rest
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
+    __syncwarp();
+    s = s2;
   }
   float* out = partials + (size_t)blockIdx.y * 4 * Mp;
 #pragma unroll
@@ -412,7 +460,8 @@ SparsePlan plan(int N, int M) {
   SparsePlan p;
   p.nblk = ceil_div(M, 2 * NB_PAIRS);
   p.npairs_p = p.nblk * NB_PAIRS;
-  p.fwd_smem = (size_t)3 * p.npairs_p * sizeof(float4) + (size_t)p.nblk * (sizeof(float4) + sizeof(float));
+  p.fwd_smem = (size_t)3 * p.npairs_p * sizeof(float4) +
+               (size_t)(p.nblk + (p.nblk + SUP - 1) / SUP) * (sizeof(float4) + sizeof(float)) + 16;
   size_t off = 0;
   p.off_recs = off; off += align_up((size_t)3 * p.npairs_p * sizeof(float4), 256);
   p.off_bb = off;   off += align_up((size_t)p.nblk * sizeof(float4), 256);

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import mixed_err
+from helpers import maxnorm_err, mixed_err
 from oracle import closed_form as cf
 
 pytestmark = pytest.mark.gpu
@@ -53,8 +53,11 @@ def test_sparse_matches_dense_and_oracle(N, Mf, Mx, coherent, perm_kind, mask):
     for level in (2, 3):
         js = be.forward_sparse(level, *args, T(c["b"]), perm, cutoff, stats).cpu().numpy()
         jd = be.forward(2, 0, level, *args, T(c["b"])).cpu().numpy()
+        ref = cf.jets2d("gaussian", c["x"], c["y"], xc.cpu().numpy(), yc.cpu().numpy(), c["h"], c["W"], c["b"])
         for a in range(js.shape[0]):
-            assert mixed_err(js[a], jd[a]) < 2e-6, (level, a, mixed_err(js[a], jd[a]))
+            # vs dense: only the summation order differs (fp32 round-off) + the tail beyond 7.5 widths
+            assert maxnorm_err(js[a], jd[a]) < 1e-5, (level, a, maxnorm_err(js[a], jd[a]))
+            assert mixed_err(js[a], ref[a]) < 3e-5, (level, a, mixed_err(js[a], ref[a]))
     assert 0 < int(stats[0]) <= 2 * (((N + 63) // 64) * 64) * (((M + 31) // 32) * 32)
     g = c["g"].copy()
     gdev = g.copy()
@@ -69,7 +72,7 @@ def test_sparse_matches_dense_and_oracle(N, Mf, Mx, coherent, perm_kind, mask):
     for a, b_, key in zip(gs, gd, ("d_xc", "d_yc", "d_h", "d_W", "d_b")):
         a, b_ = a.cpu().numpy(), b_.cpu().numpy()
         assert a.shape == b_.shape and np.all(np.isfinite(a))
-        assert mixed_err(a, b_) < 5e-6, (key, mixed_err(a, b_))
+        assert maxnorm_err(a, b_) < 1e-5, (key, maxnorm_err(a, b_))
         assert mixed_err(a, G[key]) < 3e-5, (key, mixed_err(a, G[key]))
     # deterministic (no atomics on the data path)
     gs2 = be.backward_sparse(2, *args, T(gdev), True, mask, perm, cutoff)
@@ -84,7 +87,7 @@ def test_sparse_scalar_width_and_errors():
     args = (T(c["x"]), T(c["y"]), T(c["xf"]), T(c["yf"]), T(c["xfix"]), T(c["yfix"]), T(c["h"]), T(c["W"]))
     gs = be.backward_sparse(2, *args, T(c["g"]), True, 0, None, 8.0)
     gd = be.backward(2, 0, 2, *args, T(c["g"]), True, 0)
-    assert gs[2].shape == (1,) and mixed_err(gs[2].cpu().numpy(), gd[2].cpu().numpy()) < 5e-6
+    assert gs[2].shape == (1,) and maxnorm_err(gs[2].cpu().numpy(), gd[2].cpu().numpy()) < 5e-6
     lib = _cabi.load()
     rc = lib.spinn2d_jets_fwd_sparse(1, 2, 10, 1, 0, 1, *([None] * 7), 0, *([None] * 3), 7.0, *([None] * 3), 0, None)
     assert rc == -4 and b"Gaussian" in lib.spinn_last_error()
