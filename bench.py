@@ -39,6 +39,7 @@ UNIT = "point-node evals/s"
 FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 29.0
 MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
+NCU_DRAM_BYTES_BWD_STRUCTURED = 101.061632e6 + 6.608128e6      # profiles/r01b_ncu_full.txt
 
 
 def workload_name(kind, n_points, n_nodes):
@@ -408,7 +409,12 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "kernel": "g2k1_bwd_kernel (%s upstream)" % ("general 5-row" if args.general_backward else "structured u_xx,u_yy"),
         "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
-        "frac": ach_bwd / measured_fp32, "traffic": None,
+        "frac": ach_bwd / measured_fp32,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
+        # `ncu --set full` capture (profiles/r01b_ncu_full.txt), valid for the default workload only
+        "traffic": (NCU_DRAM_BYTES_BWD_STRUCTURED if (N == 4194304 and M == 4096 and ws == 1
+                                                      and not args.general_backward) else None),
+        "traffic_algorithmic": 48.0 * (n_loc / 2) + 16.0 * M * 74 if not args.general_backward else None,
         "peak_source": "best in-run FMA probe (spinn_microbench: FFMA/FFMA2 chains, register operands, 64 warps/SM), lane-FMA/s x 2",
         "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
         "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR,
