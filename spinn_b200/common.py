@@ -169,7 +169,7 @@ class Optimizer:
     def from_args(cls, pde, nn, plotter, args):
         opt_class = {"Adam": torch.optim.Adam, "LBFGS": torch.optim.LBFGS}[args.optimizer]
         if getattr(args, "graph", False) and cls is Optimizer:
-            from .graphed import GraphedOptimizer
+            from .graphed import GraphedOptimizer                 # also data-parallel under torchrun
             cls = GraphedOptimizer
         elif cls is Optimizer and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             from .dist_optimizer import DistributedOptimizer      # one process per GPU (torchrun)

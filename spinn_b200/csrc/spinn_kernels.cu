@@ -902,6 +902,8 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const bool mixed = level == 3;
     const Tune tune = get_tune();
     const int sms = sm_count();
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
 #define SPINN_LAUNCH_FAST_FWD(P_, T_, B_, U_)                                                               \
   do {                                                                                              \
     const long long nwt = ((long long)N + 32 * P_ - 1) / (32 * P_);                                 \
@@ -909,18 +911,18 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     if (blocks > (long long)sms * B_) blocks = (long long)sms * B_;                                 \
     if (mixed) {                                                                                    \
       auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_>;                                             \
-      static bool configured = false; /* once per instantiation: not during graph capture */       \
-      if (!configured) {                                                                            \
+      static bool configured[64] = {false}; /* once per instantiation and device (not in capture) */ \
+      if (!configured[cur_dev]) {                                                                   \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
-        configured = true;                                                                          \
+        configured[cur_dev] = true;                                                                 \
       }                                                                                             \
       kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
     } else {                                                                                        \
       auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_>;                                            \
-      static bool configured = false;                                                               \
-      if (!configured) {                                                                            \
+      static bool configured[64] = {false};                                                         \
+      if (!configured[cur_dev]) {                                                                   \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
-        configured = true;                                                                          \
+        configured[cur_dev] = true;                                                                 \
       }                                                                                             \
       kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
     }                                                                                               \

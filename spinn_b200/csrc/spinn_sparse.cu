@@ -533,19 +533,21 @@ int spinn2d_jets_fwd_sparse(int kind, int level, int N, int M_free, int M_fixed,
       M, M_free, p.nblk, node_perm, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar, W, cutoff, recs, bb, r2);
   SP_LAUNCH_CHECK("pack_nodes_fwd_sparse_kernel");
   const int vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)jets) % 8 == 0) && (N % 2 == 0);
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
   const long long nwt = ((long long)N + 63) / 64;
   long long blocks = (nwt + FWD_T / 32 - 1) / (FWD_T / 32);
   const long long cap = (long long)spinn_sm_count() * 2;
   if (blocks > cap) blocks = cap;
   if (level == 3) {
     auto kfn = g2k1_fwd_sparse_kernel<true>;
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured = true; }
+    static bool configured[64] = {false};
+    if (!configured[cur_dev]) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured[cur_dev] = true; }
     kfn<<<(int)blocks, FWD_T, p.fwd_smem, s>>>(N, x, y, recs, bb, r2, p.nblk, bias, jets, vec_ok, stats);
   } else {
     auto kfn = g2k1_fwd_sparse_kernel<false>;
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured = true; }
+    static bool configured[64] = {false};
+    if (!configured[cur_dev]) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured[cur_dev] = true; }
     kfn<<<(int)blocks, FWD_T, p.fwd_smem, s>>>(N, x, y, recs, bb, r2, p.nblk, bias, jets, vec_ok, stats);
   }
   SP_LAUNCH_CHECK("g2k1_fwd_sparse_kernel");

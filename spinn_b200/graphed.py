@@ -18,15 +18,25 @@ import time
 
 import torch
 
-from .common import Optimizer
+from . import distributed
+from .dist_optimizer import DistributedOptimizer
 
 
-class GraphedOptimizer(Optimizer):
+class GraphedOptimizer(DistributedOptimizer):
+    """Single- or multi-GPU (torchrun): with WORLD_SIZE > 1 the interior points are sharded and the
+    packed gradient all-reduce (NCCL) is captured inside the graph as well."""
+
     WARMUP_STEPS = 3          # eager steps before capture (they are real training steps)
 
     def _body(self):
-        loss = self.pde.loss(self.nn)
+        loss = self._local_loss()
         loss.backward(retain_graph=True)
+        if self.world > 1:
+            import torch.distributed as dist
+            self._buf = distributed.all_reduce_gradients(list(self.nn.parameters()), average=False,
+                                                         buf=self._buf)
+            loss = loss.detach().clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         return loss
 
     def _pre_step(self):

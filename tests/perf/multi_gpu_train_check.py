@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Run under torchrun on N GPUs: trains poisson2d_sine (a) data-parallel eager and (b) data-parallel
+with --graph, and checks both loss histories against the reference's recorded single-process one.
+    python -m torch.distributed.run --nproc-per-node 2 tests/perf/multi_gpu_train_check.py
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from spinn_b200.problems import poisson2d_sine  # noqa: E402
+
+rank = int(os.environ.get("RANK", "0"))
+ref = np.load(os.path.join(ROOT, "tests", "golden", "traj_poisson2d_sine.npz"))["loss"]
+steps = 120
+for extra in ([], ["--graph"]):
+    np.random.seed(0)
+    torch.manual_seed(0)
+    app = poisson2d_sine.make_app()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        app.run(args=["--nodes", "100", "--samples", "400", "--n-train", str(steps), "--lr", "1e-3",
+                      "--tol", "1e-30", "--gpu"] + extra)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    loss = np.asarray(app.solver.loss)
+    rel = np.abs(loss - ref[:steps]) / np.abs(ref[:steps])
+    if rank == 0:
+        print(type(app.solver).__name__, "world", app.solver.world, "local interior points",
+              app.pde.p_samples[0].numel(), "max rel loss diff", float(rel.max()), "first10", float(rel[:10].max()),
+              f"{1e3 * dt / steps:.3f} ms/step incl. setup", flush=True)
+    assert rel[:10].max() < 5e-5 and rel.max() < 3e-3, (extra, rel.max())
+if rank == 0:
+    print("OK")
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.destroy_process_group()
