@@ -275,7 +275,7 @@ def main():
     trajectory("cavity", "cavity", from_mod("CavityPDE", "App2D", "SPINN2D", "CavityPlotter"),
                ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4",
                 "--n-train", "100"])
-    only(["pu", "traj:ode3_lbfgs", "traj:sine_pu", "traj:sine_fixed_h"])
+    only(["pu", "traj:ode3_lbfgs", "traj:sine_pu", "traj:sine_fixed_h", "traj:ode3_tolstop"])
 
 
 def only(names):
@@ -306,6 +306,10 @@ def only(names):
     table["traj:sine_fixed_h"] = lambda: trajectory(
         "poisson2d_sine_fixed_h", "poisson2d_sine", from_mod("Poisson2D", "App2D", "SPINN2D", "Plotter2D"),
         ["--nodes", "100", "--samples", "400", "--n-train", "60", "--lr", "1e-3", "--tol", "1e-30", "--fixed-h"])
+    table["traj:ode3_tolstop"] = lambda: trajectory(
+        "ode3_tolstop", "ode3", from_mod("ODESimple", "App1D", "SPINN1D", "Plotter1D"),
+        ["--nodes", "3", "--samples", "60", "--n-train", "2000", "--lr", "1e-3", "--tol", "2e-2",
+         "--n-skip", "20"])
     for n in names:
         table[n]()
 

@@ -391,3 +391,14 @@ def test_cutoff_flag_routes_to_the_compact_support_entry_points(oracle_backend):
     p = _ops.morton_order(xy[0], xy[1]).long()
     blocks = xy[:, p].reshape(2, 4, 16)            # 16 consecutive nodes of an 8x8 grid = a 4x4 cell
     assert float((blocks.max(-1).values - blocks.min(-1).values).max()) == 3.0
+
+
+def test_tolerance_stop_takes_effect_one_iteration_late(oracle_backend):
+    """The reference checks `err < tol` only when it reports (every n_skip) and stops one
+    iteration later (common.py:267-268,288-293): ode3 with tol=2e-2, n_skip=20 stops after 441
+    closure calls in the reference run; the mirror loop must stop at exactly the same count."""
+    ref, args = _traj("ode3_tolstop")
+    loss = _run(ode3.make_app(), args)
+    assert len(loss) == len(ref) == 441
+    rel = np.abs(loss - ref) / np.abs(ref)
+    assert rel.max() < 2e-3
