@@ -535,6 +535,11 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.kind, N, M), "parallelism": f"points sharded over {ws} GPU(s)",
                    "points": N, "nodes": M, "points_per_gpu": n_loc, "kind": args.kind,
+                   "forward": "all 5 jets for every point-node pair (dense, no cut-off)",
+                   "backward": ("general: upstream gradients for all 5 jets" if args.general_backward else
+                                "structured: this residual has upstream gradients for u_xx,u_yy only (what "
+                                "autograd hands the op through the plug-in API too); every pair evaluated; "
+                                "see general_upstream for the 5-row variant"),
                    "l2_policy": "inputs larger than L2: per step x,y 8 B + jets 20 B + gjets 20 B + packed "
                                 "point records 32 B per point (>300 MB at 4M points vs 126 MB L2)",
                    "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
