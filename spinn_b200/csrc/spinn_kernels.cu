@@ -188,19 +188,20 @@ static const BwdCfg BWD_CFGS[] = {
     {1, 128, 8, 256},  // 1
     {2, 256, 2, 256},  // 2  (default)
     {4, 128, 2, 256},  // 3
+    {1, 64, 8, 256},   // 4  (64-node tile for small node sets)
 };
 constexpr int N_FWD_CFGS = sizeof(FWD_CFGS) / sizeof(FWD_CFGS[0]);
 constexpr int N_BWD_CFGS = sizeof(BWD_CFGS) / sizeof(BWD_CFGS[0]);
 constexpr int FWD_DEFAULT = 3, BWD_DEFAULT = 2, WAVES_DEFAULT = 2;   // picked with tools/tune.py on B200
 
-struct Tune { int fwd, bwd, waves; };
+struct Tune { int fwd, bwd, waves; bool bwd_forced; };
 static Tune get_tune() {
-  Tune t = {FWD_DEFAULT, BWD_DEFAULT, WAVES_DEFAULT};
+  Tune t = {FWD_DEFAULT, BWD_DEFAULT, WAVES_DEFAULT, false};
   const char* e = getenv("SPINN_TUNE");
   if (e) {
     const char* q;
     if ((q = strstr(e, "fwd="))) t.fwd = atoi(q + 4);
-    if ((q = strstr(e, "bwd="))) t.bwd = atoi(q + 4);
+    if ((q = strstr(e, "bwd="))) { t.bwd = atoi(q + 4); t.bwd_forced = true; }
     if ((q = strstr(e, "waves="))) t.waves = atoi(q + 6);
   }
   if (t.fwd < 0 || t.fwd >= N_FWD_CFGS) t.fwd = FWD_DEFAULT;
@@ -766,8 +767,20 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
   const int Mp_gen = round_up_i(M, GEN_THREADS);
   int pc_gen = 0;
   const int c_gen = chunks_for(sms, 2, Mp_gen / GEN_THREADS, N, GEN_TILE_POINTS, 4, &pc_gen);
-  // fast path (selected variant) + worst case over all variants / wave counts up to 8
-  const BwdCfg cfg = BWD_CFGS[tune.bwd];
+  // fast path: the node tile of a CTA is Q*threads nodes; pick the variant that wastes the fewest
+  // padded node slots (relative kernel cost measured with tools/tune.py: 512-node tile 1.00,
+  // 256-node tile 1.015, 128-node tile 1.06, 64-node tile ~1.10), unless SPINN_TUNE pins one
+  if (!tune.bwd_forced) {
+    const int cand[4] = {2, 0, 1, 4};
+    const double cost[4] = {1.0, 1.015, 1.06, 1.10};
+    double best = 1e300;
+    for (int i = 0; i < 4; ++i) {
+      const BwdCfg c = BWD_CFGS[cand[i]];
+      const double w = (double)round_up_i(M, c.q * c.threads) * cost[i];
+      if (w < best) { best = w; p.variant = cand[i]; }
+    }
+  }
+  const BwdCfg cfg = BWD_CFGS[p.variant];
   const int group = cfg.q * cfg.threads;
   const int Mp_fast = round_up_i(M, group);
   int pc_fast = 0;
@@ -1021,6 +1034,7 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
       case 0: SPINN_LAUNCH_FAST_BWD(2, 128, 4, 256); break;
       case 1: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256); break;
       case 3: SPINN_LAUNCH_FAST_BWD(4, 128, 2, 256); break;
+      case 4: SPINN_LAUNCH_FAST_BWD(1, 64, 8, 256); break;
       default: SPINN_LAUNCH_FAST_BWD(2, 256, 2, 256); break;
     }
 #undef SPINN_LAUNCH_FAST_BWD

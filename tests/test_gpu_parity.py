@@ -310,3 +310,65 @@ def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
         assert np.all(np.isfinite(got)), (mask, key)
         # seeded random clouds (301+40 random centres, heavy cancellation in d_h): 1.5x the golden-case bar
         assert mixed_err(got, G[key]) < 1.5 * tol_for(kind), (mask, kind, K, key, mixed_err(got, G[key]))
+
+
+def _sweep_cases():
+    rs = np.random.RandomState(2024)
+    cases = []
+    for i in range(28):
+        dim = 2 if i % 4 else 1
+        kind = "gaussian" if i % 2 else "softplus"
+        K = int(rs.choice([1, 1, 2, 3, 4]))
+        N = int(rs.choice([1, 2, 3, 31, 64, 65, 257, 1000, 2049]))
+        Mf = int(rs.choice([0, 1, 2, 31, 63, 129, 300]))
+        Mx = int(rs.choice([0, 1, 5, 64])) if Mf else int(rs.choice([1, 7, 130]))
+        level = int(rs.randint(0, 4 if dim == 2 else 3))
+        cases.append((i, dim, kind, K, N, Mf, Mx, level))
+    return cases
+
+
+@pytest.mark.parametrize("i,dim,kind,K,N,Mf,Mx,level", _sweep_cases())
+def test_random_shape_sweep(i, dim, kind, K, N, Mf, Mx, level):
+    """Seeded sweep over awkward sizes (tiny / odd / tile-boundary N and M, every K, level, kernel,
+    1-D and 2-D, random present-masks) against the fp64 oracle."""
+    rs = np.random.RandomState(100 + i)
+    M = Mf + Mx
+    h0 = (1.0 / np.sqrt(M) if dim == 2 else 1.0 / M) * 1.5
+    x, y = rs.rand(N).astype(np.float32), rs.rand(N).astype(np.float32)
+    xf, yf = rs.rand(Mf).astype(np.float32), rs.rand(Mf).astype(np.float32)
+    xx, yx = rs.rand(Mx).astype(np.float32), rs.rand(Mx).astype(np.float32)
+    h = (h0 * (1 + 0.5 * rs.rand(M))).astype(np.float32)
+    W, b = (0.3 * rs.randn(K, M)).astype(np.float32), (0.1 * rs.randn(K)).astype(np.float32)
+    from spinn_b200 import ops
+    nj = ops.num_jets(dim, level)
+    g = rs.randn(nj, N, K).astype(np.float32)
+    mask = int(rs.randint(1, 1 << nj))
+    gm = g.copy()
+    for a in range(nj):
+        if not (mask >> a) & 1:
+            gm[a] = 0.0
+    be = backend()
+    kid = cf.kind_id(kind)
+    if dim == 2:
+        args = (T(x), T(y), T(xf), T(yf), T(xx), T(yx), T(h), T(W))
+        J = cf.jets2d(kind, x, y, np.concatenate([xf, xx]), np.concatenate([yf, yx]), h, W, b)
+        g6 = np.zeros((6, N, K)); g6[:nj] = gm
+        G = cf.grads2d(kind, x, y, np.concatenate([xf, xx]), np.concatenate([yf, yx]), h, W, g6, n_free=Mf)
+        keys = ("d_xc", "d_yc", "d_h", "d_W", "d_b")
+    else:
+        args = (T(x), None, T(xf), None, T(xx), None, T(h), T(W))
+        J = cf.jets1d(kind, x, np.concatenate([xf, xx]), h, W, b)
+        g3 = np.zeros((3, N, K)); g3[:nj] = gm
+        G = cf.grads1d(kind, x, np.concatenate([xf, xx]), h, W, g3, n_free=Mf)
+        keys = ("d_xc", None, "d_h", "d_W", "d_b")
+    jets = be.forward(dim, kid, level, *args, T(b)).cpu().numpy()
+    tol = 1.5 * tol_for(kind)
+    for a in range(nj):
+        assert mixed_err(jets[a], J[a]) < tol, (a, mixed_err(jets[a], J[a]))
+    grads = be.backward(dim, kid, level, *args, T(g), True, mask)
+    for got, key in zip(grads, keys):
+        if key is None:
+            continue
+        got = got.cpu().numpy()
+        assert got.shape == np.asarray(G[key]).shape
+        assert mixed_err(got, G[key]) < tol, (key, mixed_err(got, G[key]))
