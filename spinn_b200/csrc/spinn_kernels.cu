@@ -747,9 +747,12 @@ static int chunks_for(int sms, int waves, int groups, long long units, int tile,
   long long target = (long long)sms * blocks_per_sm * waves;
   int c = (int)((target + groups - 1) / groups);
   if (c < 1) c = 1;
+  // chunk length: whole smem tiles for large point sets; for small ones a finer granularity
+  // (the tile loop handles partial tiles) so that a few hundred points still spread over many CTAs
   long long per = (units + c - 1) / c;
-  per = (per + tile - 1) / tile * tile;
-  if (per < tile) per = tile;
+  const int gran = per >= 4LL * tile ? tile : 32;
+  per = (per + gran - 1) / gran * gran;
+  if (per < gran) per = gran;
   *per_chunk = (int)per;
   c = (int)((units + per - 1) / per);
   return c < 1 ? 1 : c;

@@ -97,8 +97,21 @@ def main(names):
     load_reference()
     torch.set_num_threads(8)
     refs = accuracy_refs()
+    extra = "--more" in names          # 8 further members (k = +-3..+-6), merged into the same file
+    names = [n for n in names if not n.startswith("--")] or list(CONFIGS)
     for name in names:
         ks = CONFIGS[name][-1]
+        path = os.path.join(HERE, f"band_{name}.npz")
+        if extra and os.path.exists(path):
+            old = np.load(path)
+            new_ks = [k for k in (3, -3, 4, -4, 5, -5, 6, -6) if k not in old["k"].tolist()]
+            rows = [run_member(name, k, refs) for k in new_ks]
+            np.savez(path, k=np.concatenate([old["k"], np.asarray(new_ks)]),
+                     iterations=np.concatenate([old["iterations"], [r["iterations"] for r in rows]]),
+                     final_loss=np.concatenate([old["final_loss"], [r["final_loss"] for r in rows]]),
+                     errors=np.concatenate([old["errors"], np.stack([r["errors"] for r in rows])]), args=old["args"])
+            print(name, "added", new_ks, [r["errors"].tolist() for r in rows], flush=True)
+            continue
         rows = [run_member(name, k, refs) for k in ks]
         np.savez(os.path.join(HERE, f"band_{name}.npz"), k=np.asarray(ks),
                  iterations=np.asarray([r["iterations"] for r in rows]),
@@ -109,4 +122,4 @@ def main(names):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or list(CONFIGS))
+    main(sys.argv[1:])

@@ -6,7 +6,10 @@ The reference's converged errors are chaotic in 1e-7 perturbations of the initia
 from 3601 to 3701 for a 2e-7 change), so the acceptance target is the BAND spanned by that ensemble,
 widened by the band's own spread; the literal 1 % comparison with the unperturbed run is recorded
 in gpurun_out/convergence.json (and asserted where the ensemble itself is tight, i.e. the cavity).
-Runs use --graph (same arithmetic, ~0.3 ms/step) so that 25 000 steps take seconds."""
+For the two chaotic configs (poisson2d_sine, irregular domain: late loss spikes move the final
+Linf by 2-3x between 1e-7-perturbed runs of the reference AND of this implementation) the median of
+a 5-member ensemble of our runs is compared.  Runs use --graph (same arithmetic, ~0.3 ms/step) so
+that 25 000 steps take seconds."""
 import importlib
 import json
 import os
@@ -37,33 +40,60 @@ def _record(name, payload):
     json.dump(data, open(path, "w"), indent=1)
 
 
-@pytest.mark.parametrize("name,modname", [("ode3", "ode3"), ("poisson2d_sine", "poisson2d_sine"),
-                                          ("irreg", "poisson2d_irreg_dom"), ("cavity", "cavity")])
-def test_converged_errors_within_reference_band(name, modname):
+def _run_member(mod, name, args, k):
+    """One full training run on the GPU (--graph), initial widths scaled by (1 + k*1e-7)."""
+    import contextlib
+    import io
+    from spinn_b200 import common
     from spinn_b200.problems import accuracy
-    errs, iters, losses, args = _band(name)
-    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
     np.random.seed(0)
     torch.manual_seed(0)
     app = mod.make_app()
-    app.run(args=args + ["--gpu", "--graph", "--n-skip", "100"])
+    p = app.setup_argparse().parse_args(args + ["--gpu", "--graph", "--n-skip", "100"])
+    common.device("cuda")
+    pde = app.pde_cls.from_args(p)
+    nn = app.nn_cls.from_args(pde, app._get_activation(p), p).to("cuda")
+    with torch.no_grad():
+        nn.layer1.h.mul_(1.0 + k * 1e-7)
+    plotter = app.plotter_cls.from_args(pde, nn, p)
+    solver = app.optimizer.from_args(pde, nn, plotter, p)
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver.solve()
     if name in ("ode3", "poisson2d_sine"):
-        got = np.asarray(app.plotter.get_error(), dtype=np.float64)
+        err = plotter.get_error()
     elif name == "irreg":
-        got = np.asarray(accuracy.fem_errors(app.nn), dtype=np.float64)
+        err = accuracy.fem_errors(nn)
     else:
-        got = np.asarray(accuracy.ghia_errors(app.nn), dtype=np.float64)
+        err = accuracy.ghia_errors(nn)
+    common.device("cpu")
+    return np.asarray(err, dtype=np.float64), len(solver.loss), solver.loss[-1]
+
+
+@pytest.mark.parametrize("name,modname,members", [
+    ("ode3", "ode3", (0,)), ("cavity", "cavity", (0,)),
+    # chaotic configs (loss spikes late in training move the final error by 2-3x from run to run,
+    # in the reference ensemble and in ours alike): compare ensemble medians
+    ("poisson2d_sine", "poisson2d_sine", (0, 1, -1, 2, -2)), ("irreg", "poisson2d_irreg_dom", (0, 1, -1, 2, -2))])
+def test_converged_errors_within_reference_band(name, modname, members):
+    errs, iters, losses, args = _band(name)
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    runs = [_run_member(mod, name, args, k) for k in members]
+    ours = np.stack([r[0] for r in runs])
+    got = np.median(ours, axis=0)
     lo, hi = errs.min(0), errs.max(0)
     spread = hi - lo
-    literal = np.abs(got - errs[0]) / errs[0]
-    _record(name, {"ours": got.tolist(), "reference_unperturbed": errs[0].tolist(),
+    literal = np.abs(ours[0] - errs[0]) / errs[0]
+    _record(name, {"ours_unperturbed": ours[0].tolist(), "ours_members": ours.tolist(), "ours_median": got.tolist(),
+                   "member_perturbations_1e-7": list(members),
+                   "reference_unperturbed": errs[0].tolist(), "reference_members": errs.tolist(),
                    "reference_band_min": lo.tolist(), "reference_band_max": hi.tolist(),
-                   "literal_relative_difference": literal.tolist(), "within_1_percent": bool((literal < 0.01).all()),
-                   "iterations": len(app.solver.loss), "reference_iterations": iters.tolist(),
-                   "final_loss": app.solver.loss[-1], "reference_final_loss": losses.tolist()})
-    # inside the ensemble band, widened by its own spread and a 5 % floor
+                   "literal_relative_difference_unperturbed": literal.tolist(),
+                   "within_1_percent": bool((literal < 0.01).all()),
+                   "iterations": [r[1] for r in runs], "reference_iterations": iters.tolist(),
+                   "final_loss": [r[2] for r in runs], "reference_final_loss": losses.tolist()})
+    # inside the reference ensemble band, widened by its own spread and a 5 % floor
     margin = np.maximum(spread, 0.05 * errs[0])
     assert np.all(got >= lo - margin) and np.all(got <= hi + margin), (name, got, lo, hi)
     if name == "cavity":        # the reference ensemble is tight here (1e-5): so must we be
-        assert np.all(literal < 0.01), (got, errs[0])
-    assert abs(len(app.solver.loss) - int(iters[0])) <= 200, (len(app.solver.loss), iters)
+        assert np.all(literal < 0.01), (ours[0], errs[0])
+    assert abs(runs[0][1] - int(iters[0])) <= 200, (runs[0][1], iters)
