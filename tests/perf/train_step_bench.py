@@ -56,7 +56,8 @@ def main():
     for name, (mod, args) in CONFIGS.items():
         fused = mod.make_app()
         ms_f, loss_f = run(fused, args, a.steps)
-        ms_g, loss_g = run(mod.make_app(), args, a.steps, extra=["--graph"])
+        # graph mode: capture (~0.2 s) happens once per solve(); use a longer run to amortise it
+        ms_g, loss_g = run(mod.make_app(), args, 10 * a.steps, extra=["--graph"])
         is1d = name == "ode3"
         pde_cls, plot_cls = fused.pde_cls, fused.plotter_cls
         dense_cls = torch_port.DenseSPINN1D if is1d else torch_port.DenseSPINN2D
