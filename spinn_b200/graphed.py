@@ -30,7 +30,10 @@ class GraphedOptimizer(DistributedOptimizer):
 
     def _body(self):
         loss = self._local_loss()
-        loss.backward(retain_graph=True)
+        # gradients for the network parameters only: the reference also accumulates (never-read,
+        # never-zeroed) .grad on the sample tensors (pde2d_base.py:91); skipping that saves kernels
+        # and keeps those buffers from growing without bound over long graphed runs
+        loss.backward(retain_graph=True, inputs=self._params)
         if self.world > 1:
             import torch.distributed as dist
             self._buf = distributed.all_reduce_gradients(list(self.nn.parameters()), average=False,
@@ -47,7 +50,7 @@ class GraphedOptimizer(DistributedOptimizer):
     def solve(self):
         if self.opt_class is not torch.optim.Adam:
             raise NotImplementedError("--graph supports the Adam optimizer only")
-        params = list(self.nn.parameters())
+        params = self._params = list(self.nn.parameters())
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("--graph needs --gpu")
