@@ -31,6 +31,38 @@
 using namespace spinn;
 
 // -----------------------------------------------------------------------------
+// TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: contiguous record tiles move
+// global -> shared memory asynchronously, issued by one thread, completion tracked by the
+// barrier's transaction count.  Source/destination 16-byte aligned, size a multiple of 16.
+// -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+constexpr unsigned TMA_CHUNK = 32768;      // bytes per bulk copy
+
+// -----------------------------------------------------------------------------
 // host-side utilities
 // -----------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -296,8 +328,21 @@ g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
   const float b0 = bias ? bias[0] : 0.f;
 
   if (single) {
-    for (int e = threadIdx.x; e < 3 * npairs; e += THREADS) sm4[e] = recs[e];
+    // the whole node-record table (48 B per node pair, 96 KB at M=4096) arrives by TMA bulk copies
+    __shared__ __align__(8) uint64_t bar;
+    const unsigned bytes = 3u * (unsigned)npairs * (unsigned)sizeof(float4);
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, bytes);
+      for (unsigned off = 0; off < bytes; off += TMA_CHUNK)
+        tma_bulk_g2s(reinterpret_cast<char*>(sm4) + off, reinterpret_cast<const char*>(recs) + off,
+                     min(TMA_CHUNK, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
   }
   for (long long it = 0; it < iters; ++it) {
     const long long wt = gw + it * nwarps;
@@ -351,7 +396,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
                 const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
   constexpr int NREC = bwd_nrec(MODE), NACC = bwd_nacc(MODE);
-  __shared__ float4 sm4[NREC * TILE];
+  // ring of point-record tiles filled by TMA bulk copies: tiles t+1.. are in flight while
+  // tile t is consumed; `full[s]` flips when the bytes of stage s have landed
+  constexpr int NS = NREC <= 3 ? 3 : 2;          // ring depth (static shared memory <= 48 KB)
+  __shared__ __align__(16) float4 ring[NS][NREC * TILE];
+  __shared__ __align__(8) uint64_t full[NS];
   const int jbase = blockIdx.x * (Q * THREADS) + threadIdx.x;
   float2 nc[Q], nd[Q], rp[Q], nrt[Q], rho[Q], nk1[Q], k2p[Q];
   float hq[Q], wq[Q];
@@ -373,11 +422,28 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
 
   const int p_begin = blockIdx.y * pairs_per_chunk;
   const int p_end = min(N2, p_begin + pairs_per_chunk);
-  for (int t0 = p_begin; t0 < p_end; t0 += TILE) {
+  const int ntiles = p_end > p_begin ? (p_end - p_begin + TILE - 1) / TILE : 0;
+  auto issue = [&](int t) {                    // thread 0 only
+    const int t0 = p_begin + t * TILE;
+    const unsigned bytes = (unsigned)(min(TILE, p_end - t0) * NREC) * (unsigned)sizeof(float4);
+    mbar_expect_tx(&full[t % NS], bytes);
+    tma_bulk_g2s(ring[t % NS], ptrecs + NREC * (size_t)t0, bytes, &full[t % NS]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NS - 1 && i < ntiles; ++i) issue(i);
+  for (int t = 0; t < ntiles; ++t) {
+    const int t0 = p_begin + t * TILE;
     const int n = min(TILE, p_end - t0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < NREC * n; e += THREADS) sm4[e] = ptrecs[NREC * (size_t)t0 + e];
-    __syncthreads();
+    const float4* sm4 = ring[t % NS];
+    // stage (t+NS-1)%NS was consumed in iteration t-1 (block-wide sync at its end): refill it now
+    if (threadIdx.x == 0 && t + NS - 1 < ntiles) issue(t + NS - 1);
+    mbar_wait(&full[t % NS], (unsigned)((t / NS) & 1));
     float2 acc[Q][NACC];
 #pragma unroll
     for (int q = 0; q < Q; ++q)
@@ -411,6 +477,7 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
+    __syncthreads();                                   // everyone is done reading this stage
   }
   // rows: 0 dc, 1 dd, 2 dh, 3 dW
   float* out = partials + (size_t)blockIdx.y * 4 * Mp;
