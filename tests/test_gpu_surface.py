@@ -92,7 +92,8 @@ def _traj(name):
     ("ode3", "ode3"), ("ode3_softplus", "ode3"),
     ("poisson2d_sine", "poisson2d_sine"), ("poisson2d_sine_softplus", "poisson2d_sine"),
     ("irreg", "poisson2d_irreg_dom"), ("cavity", "cavity"),
-    ("heat1d", "heat1d"), ("burgers1d", "burgers1d")])
+    ("heat1d", "heat1d"), ("burgers1d", "burgers1d"),
+    ("poisson2d_sine_pu", "poisson2d_sine"), ("poisson2d_sine_fixed_h", "poisson2d_sine")])
 def test_config_trajectory_on_gpu_matches_reference(name, modname):
     import importlib
     mod = importlib.import_module(f"spinn_b200.problems.{modname}")
@@ -172,3 +173,21 @@ def test_partition_of_unity_on_gpu_matches_reference(on_gpu, name):
         e_new = mixed_err(got.cpu().numpy(), c[key + "_f64"])
         e_ref = mixed_err(c[key + "_f32"], c[key + "_f64"])
         assert e_new < 5e-5 and e_new < 3 * e_ref + 1e-5, (name, key, e_new, e_ref)
+
+
+def test_cutoff_and_graph_together_follow_the_reference_trajectory():
+    """--cutoff 7 (compact-support kernels) + --graph on poisson2d_sine: with Gaussians 7 widths
+    wide of a 1/12-wide node the cut-off drops nothing measurable, so the reference's loss history
+    must still be reproduced."""
+    from spinn_b200.problems import poisson2d_sine
+    ref, args, _ = _traj("poisson2d_sine")
+    i = args.index("--n-train")
+    args[i + 1] = "120"
+    np.random.seed(0)
+    torch.manual_seed(0)
+    app = poisson2d_sine.make_app()
+    app.run(args=args + ["--gpu", "--graph", "--cutoff", "7"])
+    assert app.nn.cutoff == 7.0
+    loss = np.asarray(app.solver.loss)
+    rel = np.abs(loss - ref[:120]) / np.abs(ref[:120])
+    assert rel[:10].max() < 5e-5 and rel.max() < 3e-3, rel.max()
