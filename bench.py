@@ -39,7 +39,7 @@ UNIT = "point-node evals/s"
 FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 29.0
 MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
-NCU_DRAM_BYTES_BWD_STRUCTURED = 101.061632e6 + 6.608128e6      # profiles/r01b_ncu_full.txt
+NCU_DRAM_BYTES_BWD_STRUCTURED = 100.780544e6 + 6.395392e6      # profiles/r01d_ncu_full.txt
 
 
 def workload_name(kind, n_points, n_nodes):
@@ -411,7 +411,7 @@ def run_ours(args):
         "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
         "frac": ach_bwd / measured_fp32,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
-        # `ncu --set full` capture (profiles/r01b_ncu_full.txt), valid for the default workload only
+        # `ncu --set full` capture (profiles/r01d_ncu_full.txt), valid for the default workload only
         "traffic": (NCU_DRAM_BYTES_BWD_STRUCTURED if (N == 4194304 and M == 4096 and ws == 1
                                                       and not args.general_backward) else None),
         "traffic_algorithmic": 48.0 * (n_loc / 2) + 16.0 * M * 74 if not args.general_backward else None,
