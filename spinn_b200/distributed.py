@@ -123,6 +123,8 @@ def shard_interior(pde, rank=None, world_size=None):
         pde.rng_interior = np.arange(hi - lo)
         pde.sample_size = int(pde.sample_frac * (hi - lo))
     pde._shard = (rank, world_size, lo, hi)
+    if hasattr(pde, "on_shard"):            # per-point state that follows the slice (FD-SPINN's u0)
+        pde.on_shard()
     return pde
 
 

@@ -64,7 +64,10 @@ class GraphedOptimizer(DistributedOptimizer):
         t0 = time.perf_counter()
 
         # ---- eager warm-up on a side stream (PyTorch's capture recipe) ----
-        n_eager = min(self.WARMUP_STEPS, n_train)
+        # A later solve() on the same optimiser (FD-SPINN: one per time level) replays the step
+        # captured by the first one: same parameters, same Adam state, same static buffers.
+        graph, static_loss = getattr(self, "_captured", (None, None))
+        n_eager = min(self.WARMUP_STEPS, n_train) if graph is None else 0
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -76,14 +79,14 @@ class GraphedOptimizer(DistributedOptimizer):
                 loss_buf[i].copy_(loss.detach())
         torch.cuda.current_stream().wait_stream(side)
 
-        graph, static_loss = None, None
-        if n_train > n_eager:
+        if graph is None and n_train > n_eager:
             self.opt.zero_grad(set_to_none=True)
             self._pre_step_capture = True
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_loss = self._body()
                 self.opt.step()
+            self._captured = (graph, static_loss)
 
         err, stop, i = 1.0, False, 0
         for i in range(1, n_train + 1):

@@ -209,6 +209,8 @@ def trajectory(name, module, app_attr, args, seed=0):
            "errors": np.asarray(err, dtype=np.float64),
            "args": np.asarray(args)}
     out.update({"sd_" + k: v for k, v in sd.items()})
+    if hasattr(app.pde, "u0"):            # FD-SPINN time stepping (code/fd_spinn1d_base.py)
+        out.update(t=app.pde.t, iter=app.pde.iter, u0=app.pde.u0.detach().cpu().numpy())
     np.savez_compressed(os.path.join(HERE, f"traj_{name}.npz"), **out)
     print("wrote traj", name, "final loss", app.solver.loss[-1], "err", err)
 
@@ -275,7 +277,8 @@ def main():
     trajectory("cavity", "cavity", from_mod("CavityPDE", "App2D", "SPINN2D", "CavityPlotter"),
                ["--nodes", "100", "--samples", "2500", "--sample-frac", "0.1", "--lr", "5e-4",
                 "--n-train", "100"])
-    only(["pu", "traj:ode3_lbfgs", "traj:sine_pu", "traj:sine_fixed_h", "traj:ode3_tolstop"])
+    only(["pu", "traj:ode3_lbfgs", "traj:sine_pu", "traj:sine_fixed_h", "traj:ode3_tolstop",
+          "traj:heat1d_fd", "traj:burgers1d_fd", "traj:advection1d_fd"])
 
 
 def only(names):
@@ -310,6 +313,22 @@ def only(names):
         "ode3_tolstop", "ode3", from_mod("ODESimple", "App1D", "SPINN1D", "Plotter1D"),
         ["--nodes", "3", "--samples", "60", "--n-train", "2000", "--lr", "1e-3", "--tol", "2e-2",
          "--n-skip", "20"])
+    # FD-SPINN outer loop: a few time levels, each a short solve() on the same optimiser
+    fd = lambda cls_name: from_mod(cls_name, "AppFD1D", "SPINN1D", "FDPlotter1D")
+    fd_mod = lambda m: (setattr(m, "AppFD1D", __import__("fd_spinn1d_base").AppFD1D),
+                        setattr(m, "FDPlotter1D", __import__("fd_spinn1d_base").FDPlotter1D), m)[-1]
+    table["traj:heat1d_fd"] = lambda: trajectory(
+        "heat1d_fd", "heat1d_fd_spinn", lambda m: fd("Heat1D")(fd_mod(m)),
+        ["--nodes", "10", "--samples", "100", "--dt", "0.01", "-T", "0.03", "--lr", "1e-3", "--tol", "1.2e-2",
+         "--n-train", "150", "--n-skip", "50"])
+    table["traj:burgers1d_fd"] = lambda: trajectory(
+        "burgers1d_fd", "burgers1d_fd_spinn", lambda m: fd("Burgers1D")(fd_mod(m)),
+        ["--nodes", "40", "--samples", "400", "--dt", "0.01", "-T", "0.02", "--lr", "1e-4", "--tol", "5e-6",
+         "--n-train", "100", "--n-skip", "50"])
+    table["traj:advection1d_fd"] = lambda: trajectory(
+        "advection1d_fd", "advection1d_fd_spinn", lambda m: fd("Advection1D")(fd_mod(m)),
+        ["--nodes", "20", "--samples", "500", "--sample-frac", "0.5", "--dt", "0.0025", "-T", "0.005",
+         "--lr", "1e-4", "--tol", "1e-6", "--n-train", "100"])
     for n in names:
         table[n]()
 

@@ -113,6 +113,35 @@ def test_config_trajectory_on_gpu_matches_reference(name, modname):
         assert abs(err[2] - ref_err[2]) < 0.01 * ref_err[2] + 1e-6, (name, err, ref_err)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("name,modname", [("heat1d_fd", "heat1d_fd_spinn"), ("burgers1d_fd", "burgers1d_fd_spinn"),
+                                          ("advection1d_fd", "advection1d_fd_spinn")])
+def test_fd_spinn_time_stepping_on_gpu_matches_reference(name, modname, graph):
+    """FD-SPINN outer loop (reference fd_spinn1d_base.py:142-190) on the 1-D fused op: eager, and
+    with ONE captured training step replayed across all time levels (--graph)."""
+    import importlib
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    d = np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
+    args = [str(a) for a in d["args"]]
+    if graph and "--sample-frac" in args:
+        with pytest.raises(NotImplementedError):
+            mod.make_app().run(args=args + ["--gpu", "--graph"])
+        return
+    np.random.seed(0)
+    torch.manual_seed(0)
+    app = mod.make_app()
+    app.run(args=args + ["--gpu"] + (["--graph"] if graph else []))
+    loss, ref = np.asarray(app.solver.loss), d["loss"]
+    assert len(loss) == len(ref), (len(loss), len(ref))
+    rel = np.abs(loss - ref) / (np.abs(ref) + 1e-3 * np.abs(ref).max())
+    assert rel[:10].max() < 5e-5 and rel.max() < 5e-3, (name, rel[:10].max(), rel.max())
+    assert app.pde.iter == int(d["iter"])
+    u0 = app.pde.u0.detach().cpu().numpy()
+    assert np.abs(u0 - d["u0"]).max() < 3e-3 * np.abs(d["u0"]).max()
+    if graph:
+        assert getattr(app.solver, "_captured", (None,))[0] is not None
+
+
 @pytest.mark.parametrize("name,modname,steps", [
     ("ode3", "ode3", 120), ("poisson2d_sine", "poisson2d_sine", 80),
     ("irreg", "poisson2d_irreg_dom", 40), ("cavity", "cavity", 60)])

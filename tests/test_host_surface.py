@@ -186,6 +186,47 @@ def test_config_loss_trajectory_matches_reference(oracle_backend, name, mod, ste
     assert rel[:10].max() < 2e-5, (name, rel[:10].max())
 
 
+FD_CASES = [("heat1d_fd", "heat1d_fd_spinn"), ("burgers1d_fd", "burgers1d_fd_spinn"),
+            ("advection1d_fd", "advection1d_fd_spinn")]
+
+
+@pytest.mark.parametrize("name,modname", FD_CASES)
+def test_fd_spinn_time_stepping_matches_reference(oracle_backend, name, modname):
+    """FD-SPINN outer loop (reference fd_spinn1d_base.py:142-190): several time levels, each a
+    solve() on the same optimiser with the loss as stopping criterion; the whole concatenated loss
+    history, the clock and the carried field u0 must follow the reference's run."""
+    import importlib
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    d = np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
+    app = mod.make_app()
+    loss = _run(app, [str(a) for a in d["args"]])
+    ref = d["loss"]
+    assert len(loss) == len(ref), (len(loss), len(ref))
+    # later levels start from residuals ~1e-6 of the first level's (u ~ u0): relative to the history's
+    # scale there, plain relative elsewhere
+    rel = np.abs(loss - ref) / (np.abs(ref) + 1e-3 * np.abs(ref).max())
+    assert rel[:10].max() < 2e-5 and rel.max() < 2e-3, (name, rel[:10].max(), rel.max())
+    assert app.pde.iter == int(d["iter"]) and abs(app.pde.t - float(d["t"])) < 1e-12
+    u0 = app.pde.u0.detach().cpu().numpy()
+    # (burgers: sum(u0) = 0 up to rounding, so the first Adam step of the bias follows rounding noise)
+    assert np.abs(u0 - d["u0"]).max() < 3e-3 * np.abs(d["u0"]).max()
+    np.testing.assert_allclose(app.plotter.get_error(), d["errors"], rtol=2e-3, atol=1e-9)
+
+
+def test_fd_spinn_result_files(oracle_backend, tmp_path):
+    """model_%04d.pt / results_%04d.npz per saved level (reference fd_spinn1d_base.py:62-73)."""
+    from spinn_b200.problems import heat1d_fd_spinn
+    app = heat1d_fd_spinn.make_app()
+    app.run(args=["--nodes", "5", "--samples", "20", "--dt", "0.01", "-T", "0.04", "--t-skip", "2",
+                  "--n-train", "5", "-d", str(tmp_path / "out")])
+    names = sorted(os.listdir(tmp_path / "out"))
+    assert names == ["model_0000.pt", "model_0002.pt", "model_0004.pt",
+                     "results_0000.npz", "results_0002.npz", "results_0004.npz"]
+    r = np.load(tmp_path / "out" / "results_0002.npz")
+    assert set(r.files) == {"x", "y", "y_exact", "t", "iter"} and int(r["iter"]) == 2
+    assert abs(float(r["t"]) - 0.02) < 1e-12
+
+
 # ---- the reference's UNCHANGED problem files driving our network (build container only) ----
 REF = "/root/reference/code"
 
@@ -223,18 +264,27 @@ for name, mod, cls, appn, nn_name, pl, args in [
     app = getattr(mod, appn)(pde_cls=getattr(mod, cls), nn_cls=getattr(mod, nn_name), plotter_cls=getattr(mod, pl))
     app.run(args=args)
     out[name] = np.asarray(app.solver.loss)
+# the reference's own FD-SPINN driver (fd_spinn1d_base.AppFD1D.iterate) on our Optimizer / SPINN1D
+import heat1d_fd_spinn, fd_spinn1d_base
+np.random.seed(0); torch.manual_seed(0)
+app = fd_spinn1d_base.AppFD1D(pde_cls=heat1d_fd_spinn.Heat1D, nn_cls=heat1d_fd_spinn.SPINN1D,
+                              plotter_cls=fd_spinn1d_base.FDPlotter1D)
+app.run(args=%(fd_args)r)
+out["heat1d_fd"] = np.asarray(app.solver.loss)
 np.savez(sys.argv[1], **out)
-''' % {"ref": REF, "root": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))}
+''' % {"ref": REF, "root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+       "fd_args": _traj("heat1d_fd")[1]}
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         f = os.path.join(td, "out.npz")
         subprocess.check_call([sys.executable, "-c", code, f], stdout=subprocess.DEVNULL)
         got = np.load(f)
-        for name in ("poisson2d_sine", "cavity", "ode3", "heat1d", "burgers1d"):
+        assert len(got["heat1d_fd"]) == len(_traj("heat1d_fd")[0])
+        for name in ("poisson2d_sine", "cavity", "ode3", "heat1d", "burgers1d", "heat1d_fd"):
             ref, _ = _traj(name)
             n = len(got[name])
             rel = np.abs(got[name] - ref[:n]) / np.abs(ref[:n])
-            assert rel.max() < 1e-4, (name, rel.max())
+            assert rel.max() < (5e-4 if name == "heat1d_fd" else 1e-4), (name, rel.max())   # 302 steps vs <= 50
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
