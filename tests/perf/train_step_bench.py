@@ -56,7 +56,7 @@ def main():
     for name, (mod, args) in CONFIGS.items():
         fused = mod.make_app()
         ms_f, loss_f = run(fused, args, a.steps)
-        # graph mode: capture (~0.2 s) happens once per solve(); use a longer run to amortise it
+        # graph mode: the step captured by the first solve() is replayed by the timed one
         ms_g, loss_g = run(mod.make_app(), args, 10 * a.steps, extra=["--graph"])
         is1d = name == "ode3"
         pde_cls, plot_cls = fused.pde_cls, fused.plotter_cls
@@ -68,7 +68,33 @@ def main():
                      "speedup_eager": ms_d / ms_f, "speedup_graphed": ms_d / ms_g,
                      "loss_fused": loss_f, "loss_graphed": loss_g, "loss_dense": loss_d}
         print(name, json.dumps(out[name]), flush=True)
+    out["heat1d_fd_spinn"] = fd_run(a.steps)
+    print("heat1d_fd_spinn", json.dumps(out["heat1d_fd_spinn"]), flush=True)
     print(json.dumps(out))
+
+
+def fd_run(steps):
+    """FD-SPINN outer loop (10 time levels x `steps` training steps, no tolerance stop): wall time
+    of the whole App.run per training step, fused eager / fused --graph / dense eager."""
+    from spinn_b200.problems import heat1d_fd_spinn as fd
+    from spinn_b200.problems.fd_spinn1d_base import AppFD1D
+    args = ["--nodes", "10", "--samples", "100", "--dt", "0.01", "-T", "0.1", "--lr", "1e-3", "--tol", "1e-30",
+            "--gpu", "--n-train", str(steps), "--n-skip", str(10 ** 9)]
+    res = {}
+    dense = AppFD1D(pde_cls=fd.Heat1D, nn_cls=torch_port.DenseSPINN1D, plotter_cls=fd.FDPlotter1D)
+    for tag, app, extra in (("fused", fd.make_app(), []), ("fused_graphed", fd.make_app(), ["--graph"]),
+                            ("dense_eager_same_gpu", dense, [])):
+        np.random.seed(0)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            app.run(args=args + extra)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        res[tag + "_ms_per_step"] = 1e3 * dt / (10 * steps)
+        res["linf_" + tag] = float(app.plotter.get_error()[2])
+    return res
 
 
 if __name__ == "__main__":

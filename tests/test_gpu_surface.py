@@ -137,7 +137,10 @@ def test_fd_spinn_time_stepping_on_gpu_matches_reference(name, modname, graph):
     assert rel[:10].max() < 5e-5 and rel.max() < 5e-3, (name, rel[:10].max(), rel.max())
     assert app.pde.iter == int(d["iter"])
     u0 = app.pde.u0.detach().cpu().numpy()
-    assert np.abs(u0 - d["u0"]).max() < 3e-3 * np.abs(d["u0"]).max()
+    # burgers: sum(u0) = 0 up to rounding, so Adam moves the bias by +-lr per step along the SIGN of
+    # rounding noise for the first steps (in the reference too) -> absolute slack of a few lr
+    lr = float(args[args.index("--lr") + 1])
+    assert np.abs(u0 - d["u0"]).max() < max(3e-3 * np.abs(d["u0"]).max(), 10 * lr)
     if graph:
         assert getattr(app.solver, "_captured", (None,))[0] is not None
 
