@@ -34,12 +34,12 @@ METRIC = "point-node evals/sec for fused residual fwd+bwd"
 UNIT = "point-node evals/s"
 # algorithmic flops per point-node pair (FMA = 2).  General path: SURVEY.md 8(d): 23 fwd + 53 bwd
 # (13 recompute + 40) = 76.  The benchmarked Poisson residual only has u_xx,u_yy upstream
-# gradients, so its backward runs the structured variant: 9 (geometry) + 20 = 29 flops
-# (instruction list in spinn_math.cuh:g2_bwd_pair_lapl) -> 52 per pair.
-FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 29.0
+# gradients, so its backward runs the structured variant: 8 (geometry) + 17 = 25 flops in 16
+# instructions (spinn_math.cuh:g2_bwd_pair_lapl) -> 48 per pair.
+FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 25.0
 MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
-NCU_DRAM_BYTES_BWD_STRUCTURED = 100.780544e6 + 6.395392e6      # profiles/r01d_ncu_full.txt
+NCU_DRAM_BYTES_BWD_STRUCTURED = None                            # set from profiles/r01f_ncu_full.txt
 
 
 def workload_name(kind, n_points, n_nodes):
@@ -411,10 +411,13 @@ def run_ours(args):
         "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
         "frac": ach_bwd / measured_fp32,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
-        # `ncu --set full` capture (profiles/r01d_ncu_full.txt), valid for the default workload only
+        # `ncu --set full` capture (profiles/r01f_ncu_full.txt), valid for the default workload only
         "traffic": (NCU_DRAM_BYTES_BWD_STRUCTURED if (N == 4194304 and M == 4096 and ws == 1
                                                       and not args.general_backward) else None),
-        "traffic_algorithmic": 48.0 * (n_loc / 2) + 16.0 * M * 74 if not args.general_backward else None,
+        # point-pair records (4 x 16 B) read once + per-chunk partial sums (4 rows x M floats) written;
+        # chunks = 2 waves x SMs x 2 CTAs/SM / node groups of 1024
+        "traffic_algorithmic": (64.0 * (n_loc / 2) + 16.0 * M * (2 * SMS * 2 // max(1, -(-M // 1024)))
+                                if not args.general_backward else None),
         "peak_source": "best in-run FMA probe (spinn_microbench: FFMA/FFMA2 chains, register operands, 64 warps/SM), lane-FMA/s x 2",
         "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
         "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR,

@@ -58,10 +58,15 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
     } else if (WHICH == 10) {    // MUFU.EX2
 #pragma unroll
       for (int k = 0; k < 8; ++k) { a[k].x = ex2f_fast(a[k].x); a[k].y = ex2f_fast(a[k].y); }
-    } else if (WHICH == 11) {    // FFMA2 distinct + 1 MUFU per 7 FFMA2 (forward-kernel mix)
+    } else if (WHICH == 11 || WHICH == 13 || WHICH == 14) {
+      // 16 FFMA2 (broadcast operand form) + 0 / 2 / 4 MUFU.EX2 per iteration: what does one
+      // MUFU warp-instruction cost the FMA pipe?  (the kernels run 2 MUFU per 14..20 FFMA2)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = f2fma(b[k], c[k], a[k]);
-      b[it & 7].x = ex2f_fast(-fabsf(b[it & 7].x));
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = f2fma(b[k], f2dup(m.x), a[k]);
+      if (WHICH >= 13) { c[0].x = ex2f_fast(-c[0].x); c[0].y = ex2f_fast(-c[0].y); }
+      if (WHICH == 14) { c[1].x = ex2f_fast(-c[1].x); c[1].y = ex2f_fast(-c[1].y); }
     } else if (WHICH == 12) {    // FFMA2 where b, c reused across two consecutive instrs (reuse cache)
 #pragma unroll
       for (int k = 0; k < 8; k += 2) { a[k] = f2fma(b[k], c[k], a[k]); a[k + 1] = f2fma(b[k], c[k], a[k + 1]); }
@@ -69,7 +74,7 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
   }
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y + b[k].x;
+  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y + b[k].x + c[k].x + c[k].y;
   if (s == 123.456f) sink[0] = s;
 }
 
@@ -90,8 +95,10 @@ extern "C" int spinn_microbench(int which, int iters, int blocks, int threads, c
     case 8: probe_kernel<8><<<blocks, threads, 0, s>>>(iters, in, sink); break;
     case 9: probe_kernel<9><<<blocks, threads, 0, s>>>(iters, in, sink); break;
     case 10: probe_kernel<10><<<blocks, threads, 0, s>>>(iters, in, sink); break;
-    case 11: probe_kernel<11><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 11: probe_kernel<11><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 32.0; break;
     case 12: probe_kernel<12><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 13: probe_kernel<13><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 32.0; break;
+    case 14: probe_kernel<14><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 32.0; break;
     default: return -1;
   }
   if (lane_ops) *lane_ops = lanes * per_iter;

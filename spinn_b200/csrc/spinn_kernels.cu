@@ -166,7 +166,7 @@ __global__ void pack_nodes_g2fwd_kernel(int M, int Mfree, int npairs,
 
 // fast backward records: one per POINT PAIR (i, i+1), bwd_nrec(MODE) float4 each:
 //   BWD_ALL : {x_i,x_i1,y_i,y_i1} {g0,g0',g1,g1'} {g2,g2',g3,g3'} {g4,g4',0,0}
-//   BWD_LAPL: {x..,y..} {g3,g3',g4,g4'} {g3+g4,(g3+g4)',0,0}
+//   BWD_LAPL: {x..,y..} {D,D',g4,g4'} {m,m',k3,k3'} {k4,k4',0,0}   (g2_lapl_point)
 //   BWD_U   : {x..,y..} {g0,g0',0,0}
 // rows of g whose bit in `mask` is clear are never read (they count as zero).
 template <int MODE>
@@ -196,8 +196,10 @@ __global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict_
     r[2] = make_float4(a[2], b[2], a[3], b[3]);
     r[3 % NREC] = make_float4(a[4], b[4], 0.f, 0.f);
   } else if (MODE == BWD_LAPL) {
-    r[1] = make_float4(a[3], b[3], a[4], b[4]);
-    r[2 % NREC] = make_float4(a[3] + a[4], b[3] + b[4], 0.f, 0.f);
+    const G2LaplPoint ca = g2_lapl_point(a[3], a[4]), cb = g2_lapl_point(b[3], b[4]);
+    r[1] = make_float4(ca.D, cb.D, ca.g4, cb.g4);
+    r[2 % NREC] = make_float4(ca.m, cb.m, ca.k3, cb.k3);
+    r[3 % NREC] = make_float4(ca.k4, cb.k4, 0.f, 0.f);
   } else {
     r[1] = make_float4(a[0], b[0], 0.f, 0.f);
   }
@@ -221,6 +223,9 @@ static const BwdCfg BWD_CFGS[] = {
     {2, 256, 2, 256},  // 2  (default)
     {4, 128, 2, 256},  // 3
     {1, 64, 8, 256},   // 4  (64-node tile for small node sets)
+    {4, 256, 2, 256},  // 5  (1024-node tile; two node-pair streams per thread in the structured modes)
+    {2, 256, 4, 256},  // 6  (as 2 with 64 registers/thread, 4 CTAs/SM)
+    {4, 128, 3, 256},  // 7
 };
 constexpr int N_FWD_CFGS = sizeof(FWD_CFGS) / sizeof(FWD_CFGS[0]);
 constexpr int N_BWD_CFGS = sizeof(BWD_CFGS) / sizeof(BWD_CFGS[0]);
@@ -396,29 +401,51 @@ __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
                 const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
   constexpr int NREC = bwd_nrec(MODE), NACC = bwd_nacc(MODE);
+  // Lane assignment.  General mode: the two lanes of a packed instruction are the two POINTS of a
+  // record pair (node constants are scalar-broadcast operands).  Structured modes with an even
+  // number of nodes per thread: the two lanes are two adjacent NODES and the per-point constants
+  // (5 of them in the (u_xx,u_yy) mode) are the scalar-broadcast operands -- an FFMA2 with three
+  // full register-pair operands issues at half rate (tools/microbench.py probe 3), and this
+  // assignment leaves only the three accumulate-products in that class.
+  constexpr bool LN = (MODE != BWD_ALL) && (Q % 2 == 0);
+  constexpr int QS = LN ? Q / 2 : Q;             // instruction streams per thread
   // ring of point-record tiles filled by TMA bulk copies: tiles t+1.. are in flight while
   // tile t is consumed; `full[s]` flips when the bytes of stage s have landed
   constexpr int NS = NREC <= 3 ? 3 : 2;          // ring depth (static shared memory <= 48 KB)
   __shared__ __align__(16) float4 ring[NS][NREC * TILE];
   __shared__ __align__(8) uint64_t full[NS];
-  const int jbase = blockIdx.x * (Q * THREADS) + threadIdx.x;
-  float2 nc[Q], nd[Q], rp[Q], nrt[Q], rho[Q], nk1[Q], k2p[Q];
+  const int jblock = blockIdx.x * (Q * THREADS);
+  float2 nc[QS], nd[QS], rp[QS], nrt[QS], rho[QS], nk1[QS], k2p[QS];
   float hq[Q], wq[Q];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int j = jbase + q * THREADS;
-    const float c = soa[j], d = soa[(size_t)Mp + j];
-    hq[q] = soa[2 * (size_t)Mp + j];
-    wq[q] = soa[4 * (size_t)Mp + j];
-    const G2BwdNode n = g2_bwd_node(c, d, hq[q]);
-    nc[q] = f2dup(n.nc); nd[q] = f2dup(n.nd); rp[q] = f2dup(n.rp); nrt[q] = f2dup(n.nrt);
-    rho[q] = f2dup(n.rho); nk1[q] = f2dup(n.nk1); k2p[q] = f2dup(n.k2p);
+  for (int q = 0; q < QS; ++q) {
+    if (LN) {                                    // nodes j, j+1 in the two lanes
+      const int j = jblock + 2 * (q * THREADS + threadIdx.x);
+      const float2 c = *reinterpret_cast<const float2*>(soa + j);
+      const float2 d = *reinterpret_cast<const float2*>(soa + (size_t)Mp + j);
+      const float2 h = *reinterpret_cast<const float2*>(soa + 2 * (size_t)Mp + j);
+      const float2 w = *reinterpret_cast<const float2*>(soa + 4 * (size_t)Mp + j);
+      hq[(2 * q) % Q] = h.x; hq[(2 * q + 1) % Q] = h.y;
+      wq[(2 * q) % Q] = w.x; wq[(2 * q + 1) % Q] = w.y;
+      const G2BwdNode n0 = g2_bwd_node(c.x, d.x, h.x), n1 = g2_bwd_node(c.y, d.y, h.y);
+      nc[q] = f2(n0.nc, n1.nc); nd[q] = f2(n0.nd, n1.nd); rp[q] = f2(n0.rp, n1.rp);
+      nrt[q] = f2(n0.nrt, n1.nrt); rho[q] = f2(n0.rho, n1.rho); nk1[q] = f2(n0.nk1, n1.nk1);
+      k2p[q] = f2(n0.k2p, n1.k2p);
+    } else {
+      const int j = jblock + threadIdx.x + q * THREADS;
+      const float c = soa[j], d = soa[(size_t)Mp + j];
+      hq[q % Q] = soa[2 * (size_t)Mp + j];
+      wq[q % Q] = soa[4 * (size_t)Mp + j];
+      const G2BwdNode n = g2_bwd_node(c, d, hq[q % Q]);
+      nc[q] = f2dup(n.nc); nd[q] = f2dup(n.nd); rp[q] = f2dup(n.rp); nrt[q] = f2dup(n.nrt);
+      rho[q] = f2dup(n.rho); nk1[q] = f2dup(n.nk1); k2p[q] = f2dup(n.k2p);
+    }
   }
-  float tot[Q][NACC];
+  float2 tot[QS][NACC];                          // LN: per-lane (= per-node) sums; else .x only
 #pragma unroll
-  for (int q = 0; q < Q; ++q)
+  for (int q = 0; q < QS; ++q)
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) tot[q][a] = 0.f;
+    for (int a = 0; a < NACC; ++a) tot[q][a] = f2(0.f, 0.f);
 
   const int p_begin = blockIdx.y * pairs_per_chunk;
   const int p_end = min(N2, p_begin + pairs_per_chunk);
@@ -444,9 +471,9 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
     // stage (t+NS-1)%NS was consumed in iteration t-1 (block-wide sync at its end): refill it now
     if (threadIdx.x == 0 && t + NS - 1 < ntiles) issue(t + NS - 1);
     mbar_wait(&full[t % NS], (unsigned)((t / NS) & 1));
-    float2 acc[Q][NACC];
+    float2 acc[QS][NACC];
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
+    for (int q = 0; q < QS; ++q)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) acc[q][a] = f2(0.f, 0.f);
 #pragma unroll 2
@@ -458,38 +485,77 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
         const float2 g0 = f2(B.x, B.y), g1 = f2(B.z, B.w), g2 = f2(C.x, C.y), g3 = f2(C.z, C.w);
         const float2 g4 = f2(D.x, D.y);
 #pragma unroll
-        for (int q = 0; q < Q; ++q)
+        for (int q = 0; q < QS; ++q)
           g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q],
                               k2p[q], acc[q]);
       } else if (MODE == BWD_LAPL) {
-        const float2 C = *reinterpret_cast<const float2*>(&sm4[NREC * p + 2 % NREC]);
-        const float2 g3 = f2(B.x, B.y), g4 = f2(B.z, B.w);
+        const float4 C = sm4[NREC * p + 2 % NREC];
+        const float2 k4 = *reinterpret_cast<const float2*>(&sm4[NREC * p + 3 % NREC]);
+        if (LN) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q)
-          g2_bwd_pair_lapl(x2, y2, g3, g4, C, nc[q], nd[q], rp[q], acc[q]);
+          for (int q = 0; q < QS; ++q) {
+            g2_bwd_pair_lapl(f2dup(A.x), f2dup(A.z), f2dup(B.x), f2dup(B.z), f2dup(C.x), f2dup(C.z),
+                             f2dup(k4.x), nc[q], nd[q], rp[q], acc[q]);
+            g2_bwd_pair_lapl(f2dup(A.y), f2dup(A.w), f2dup(B.y), f2dup(B.w), f2dup(C.y), f2dup(C.w),
+                             f2dup(k4.y), nc[q], nd[q], rp[q], acc[q]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < QS; ++q)
+            g2_bwd_pair_lapl(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), f2(C.z, C.w), k4, nc[q],
+                             nd[q], rp[q], acc[q]);
+        }
       } else {
-        const float2 g0 = f2(B.x, B.y);
+        if (LN) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) g2_bwd_pair_u(x2, y2, g0, nc[q], nd[q], rp[q], acc[q]);
+          for (int q = 0; q < QS; ++q) {
+            g2_bwd_pair_u(f2dup(A.x), f2dup(A.z), f2dup(B.x), nc[q], nd[q], rp[q], acc[q]);
+            g2_bwd_pair_u(f2dup(A.y), f2dup(A.w), f2dup(B.y), nc[q], nd[q], rp[q], acc[q]);
+          }
+        } else {
+          const float2 g0 = f2(B.x, B.y);
+#pragma unroll
+          for (int q = 0; q < QS; ++q) g2_bwd_pair_u(x2, y2, g0, nc[q], nd[q], rp[q], acc[q]);
+        }
       }
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
+    for (int q = 0; q < QS; ++q)
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) tot[q][a] += acc[q][a].x + acc[q][a].y;
+      for (int a = 0; a < NACC; ++a) {
+        if (LN) { tot[q][a].x += acc[q][a].x; tot[q][a].y += acc[q][a].y; }
+        else tot[q][a].x += acc[q][a].x + acc[q][a].y;
+      }
     __syncthreads();                                   // everyone is done reading this stage
   }
   // rows: 0 dc, 1 dd, 2 dh, 3 dW
   float* out = partials + (size_t)blockIdx.y * 4 * Mp;
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int j = jbase + q * THREADS;
-    float dW, dc, dd, dh;
-    g2_bwd_finish_m<MODE>(hq[q], wq[q], tot[q], &dW, &dc, &dd, &dh);
-    out[j] = dc;
-    out[(size_t)Mp + j] = dd;
-    out[2 * (size_t)Mp + j] = dh;
-    out[3 * (size_t)Mp + j] = dW;
+  for (int q = 0; q < QS; ++q) {
+    if (LN) {
+      const int j = jblock + 2 * (q * THREADS + threadIdx.x);
+      float t0[NACC], t1[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) { t0[a] = tot[q][a].x; t1[a] = tot[q][a].y; }
+      float2 dW, dc, dd, dh;
+      g2_bwd_finish_m<MODE>(hq[(2 * q) % Q], wq[(2 * q) % Q], t0, &dW.x, &dc.x, &dd.x, &dh.x);
+      g2_bwd_finish_m<MODE>(hq[(2 * q + 1) % Q], wq[(2 * q + 1) % Q], t1, &dW.y, &dc.y, &dd.y, &dh.y);
+      *reinterpret_cast<float2*>(out + j) = dc;
+      *reinterpret_cast<float2*>(out + (size_t)Mp + j) = dd;
+      *reinterpret_cast<float2*>(out + 2 * (size_t)Mp + j) = dh;
+      *reinterpret_cast<float2*>(out + 3 * (size_t)Mp + j) = dW;
+    } else {
+      const int j = jblock + threadIdx.x + q * THREADS;
+      float t0[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) t0[a] = tot[q][a].x;
+      float dW, dc, dd, dh;
+      g2_bwd_finish_m<MODE>(hq[q % Q], wq[q % Q], t0, &dW, &dc, &dd, &dh);
+      out[j] = dc;
+      out[(size_t)Mp + j] = dd;
+      out[2 * (size_t)Mp + j] = dh;
+      out[3 * (size_t)Mp + j] = dW;
+    }
   }
 }
 
@@ -825,7 +891,7 @@ static int chunks_for(int sms, int waves, int groups, long long units, int tile,
   return c < 1 ? 1 : c;
 }
 
-static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool worst) {
+static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool worst, int mode = BWD_ALL) {
   BwdPlan p;
   p.fast = bwd_is_fast(dim, kind, level, K);
   const Tune tune = get_tune();
@@ -840,11 +906,13 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
   // fast path: the node tile of a CTA is Q*threads nodes; pick the variant that wastes the fewest
   // padded node slots (relative kernel cost measured with tools/tune.py: 512-node tile 1.00,
   // 256-node tile 1.015, 128-node tile 1.06, 64-node tile ~1.10), unless SPINN_TUNE pins one
+  // The structured modes also have a 1024-node tile (two node-pair streams per thread, 3 % faster
+  // than the 512-node tile at M = 4096).
   if (!tune.bwd_forced) {
-    const int cand[4] = {2, 0, 1, 4};
-    const double cost[4] = {1.0, 1.015, 1.06, 1.10};
+    const int cand[5] = {2, 0, 1, 4, 5};
+    const double cost[5] = {1.0, 1.015, 1.06, 1.10, 0.97};
     double best = 1e300;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < (mode == BWD_ALL ? 4 : 5); ++i) {
       const BwdCfg c = BWD_CFGS[cand[i]];
       const double w = (double)round_up_i(M, c.q * c.threads) * cost[i];
       if (w < best) { best = w; p.variant = cand[i]; }
@@ -1055,7 +1123,8 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
   if (N > 0 && (!x || (dim == 2 && !y) || !gj))
     return fail(SPINN_E_BADARG, "null point/gradient pointer in jets_bwd");
   cudaStream_t s = (cudaStream_t)stream;
-  const BwdPlan p = plan_bwd(dim, kind, level, N, M, K, false);
+  if (present_mask < 0) return fail(SPINN_E_BADARG, "present_mask must be >= 0");
+  const BwdPlan p = plan_bwd(dim, kind, level, N, M, K, false, bwd_mode_for(effective_mask(dim, level, present_mask)));
   if (!ws || ws_bytes < p.ws_bytes)
     return fail(SPINN_E_WORKSPACE, "backward workspace too small: %zu < %zu", ws_bytes, p.ws_bytes);
   char* base = (char*)ws;
@@ -1105,6 +1174,9 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
       case 1: SPINN_LAUNCH_FAST_BWD(1, 128, 8, 256); break;
       case 3: SPINN_LAUNCH_FAST_BWD(4, 128, 2, 256); break;
       case 4: SPINN_LAUNCH_FAST_BWD(1, 64, 8, 256); break;
+      case 5: SPINN_LAUNCH_FAST_BWD(4, 256, 2, 256); break;
+      case 6: SPINN_LAUNCH_FAST_BWD(2, 256, 4, 256); break;
+      case 7: SPINN_LAUNCH_FAST_BWD(4, 128, 3, 256); break;
       default: SPINN_LAUNCH_FAST_BWD(2, 256, 2, 256); break;
     }
 #undef SPINN_LAUNCH_FAST_BWD

@@ -224,37 +224,48 @@ SP_HD void g2_bwd_finish(float h, float W, float aW, float nAc, float nAd, float
 // configs -- and only u present -- Dirichlet boundary penalties.  With the absent terms removed
 // every remaining term shares one node-constant factor, which moves out of the sum over points.
 enum { BWD_ALL = 0, BWD_LAPL = 1, BWD_U = 2 };
-SP_HD constexpr int bwd_nrec(int mode) { return mode == BWD_ALL ? 4 : mode == BWD_LAPL ? 3 : 2; }
+SP_HD constexpr int bwd_nrec(int mode) { return mode == BWD_U ? 2 : 4; }
 SP_HD constexpr int bwd_nacc(int mode) { return mode == BWD_ALL ? 4 : mode == BWD_LAPL ? 5 : 4; }
 
-// only g3 (u_xx), g4 (u_yy) and g34 = g3+g4:  q = g3 hx + g4 hy
-//   acc0 += E q;  acc1 += E xi (q - 2 s2 g3);  acc2 += E eta (q - 2 s2 g4);
-//   acc3 += E q (t - 2 s2);  acc4 += E g34            (s2 = sigma^2)
+// only g3 (u_xx), g4 (u_yy).  With a = xi^2, s = xi^2 + eta^2, phi = 2^{-s} (= E/e) and the
+// per-POINT constants D = g3-g4, m = -s2 (g3+g4), k3 = -2 s2 g3, k4 = -2 s2 g4 (s2 = sigma^2;
+// formed once per point by the pack kernel):
+//   q = g3 hx + g4 hy = D a + g4 s + m
+//   acc0 += phi q;  acc1 += xi phi (q + k3);  acc2 += eta phi (q + k4);
+//   acc3 += phi q s;  acc4 += phi m                                  -> 16 instructions
+// (the shifts t - 2 s2 = s - 4 s2 and the factor e are applied once per node, g2_bwd_finish_m)
 template <int PK = 1, int PA = 1>
-SP_HD void g2_bwd_pair_lapl(float2 x2, float2 y2, float2 g3, float2 g4, float2 g34,
+SP_HD void g2_bwd_pair_lapl(float2 x2, float2 y2, float2 D, float2 g4, float2 m, float2 k3, float2 k4,
                             float2 nc, float2 nd, float2 rp, float2* acc) {
-  const float2 nsig2 = f2dup(-SIG2_F), n2sig2 = f2dup(-2.0f * SIG2_F);
   float2 X  = f2add<PK>(x2, nc);
   float2 Y  = f2add<PK>(y2, nd);
   float2 xi = f2mul<PK>(X, rp);
   float2 et = f2mul<PK>(Y, rp);
-  float2 hx = f2fma<PK>(xi, xi, nsig2);
-  float2 hy = f2fma<PK>(et, et, nsig2);
-  float2 t  = f2add<PK>(hx, hy);
-  float2 E  = f2ex2neg(t);
-  float2 q  = f2mul<PK>(g3, hx);
-  q = f2fma<PK>(g4, hy, q);
-  float2 Eq = f2mul<PK>(E, q);
-  float2 cx = f2fma<PK>(n2sig2, g3, q);
-  float2 cy = f2fma<PK>(n2sig2, g4, q);
-  float2 Ex = f2mul<PK>(E, xi);
-  float2 Ey = f2mul<PK>(E, et);
-  float2 u  = f2add<PK>(t, n2sig2);
-  acc[0] = f2add<PA>(acc[0], Eq);
-  acc[1] = f2fma<PA>(Ex, cx, acc[1]);
-  acc[2] = f2fma<PA>(Ey, cy, acc[2]);
-  acc[3] = f2fma<PA>(Eq, u, acc[3]);
-  acc[4] = f2fma<PA>(E, g34, acc[4]);
+  float2 a  = f2mul<PK>(xi, xi);
+  float2 s  = f2fma<PK>(et, et, a);
+  float2 ph = f2ex2neg(s);
+  float2 q  = f2fma<PK>(g4, s, m);
+  q = f2fma<PK>(D, a, q);
+  float2 Pq = f2mul<PK>(ph, q);
+  float2 vx = f2fma<PK>(ph, k3, Pq);
+  float2 vy = f2fma<PK>(ph, k4, Pq);
+  acc[0] = f2add<PA>(acc[0], Pq);
+  acc[1] = f2fma<PA>(xi, vx, acc[1]);
+  acc[2] = f2fma<PA>(et, vy, acc[2]);
+  acc[3] = f2fma<PA>(Pq, s, acc[3]);
+  acc[4] = f2fma<PA>(ph, m, acc[4]);
+}
+
+// per-point constants of the (u_xx, u_yy)-only backward, from the two upstream gradients
+struct G2LaplPoint { float D, g4, m, k3, k4; };
+SP_HD G2LaplPoint g2_lapl_point(float g3, float g4) {
+  G2LaplPoint c;
+  c.D = g3 - g4;
+  c.g4 = g4;
+  c.m = -SIG2_F * (g3 + g4);
+  c.k3 = -2.0f * SIG2_F * g3;
+  c.k4 = -2.0f * SIG2_F * g4;
+  return c;
 }
 
 // only g0 (u):  phi = 2^{-(xi^2+eta^2)} directly;  acc0 += phi g0; acc1 += phi g0 xi;
@@ -282,12 +293,14 @@ SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* d
   if (MODE == BWD_ALL) {
     g2_bwd_finish(h, W, a[0], a[1], a[2], a[3], dW, dc, dd, dh);
   } else if (MODE == BWD_LAPL) {
+    // accumulators are in units of phi = E/e; a[3] holds sum(phi q s), the general form needs
+    // sum(phi q (s - 4 s2)); a[4] = sum(phi m) = -s2 sum(phi (g3+g4))
     const double rho = rt * rt;
-    const double f = (double)W * rt * rho * INV_E_D;
-    *dW = (float)(rho * INV_E_D * (double)a[0]);
+    const double f = (double)W * rt * rho;
+    *dW = (float)(rho * (double)a[0]);
     *dc = (float)(f * (double)a[1]);
     *dd = (float)(f * (double)a[2]);
-    *dh = (float)(f / SIG_D * ((double)a[3] - 2.0 * SIG2_D * SIG2_D * (double)a[4]));
+    *dh = (float)(f / SIG_D * ((double)a[3] - 4.0 * SIG2_D * (double)a[0] + 2.0 * SIG2_D * (double)a[4]));
   } else {
     const double f = (double)W * rt;
     *dW = a[0];

@@ -248,8 +248,10 @@ pack_points_sparse_kernel(int N, int N2, const float* __restrict__ x, const floa
     r[2] = make_float4(a[2], b[2], a[3], b[3]);
     r[3 % NREC] = make_float4(a[4], b[4], 0.f, 0.f);
   } else if (MODE == BWD_LAPL) {
-    r[1] = make_float4(a[3], b[3], a[4], b[4]);
-    r[2 % NREC] = make_float4(a[3] + a[4], b[3] + b[4], 0.f, 0.f);
+    const G2LaplPoint ca = g2_lapl_point(a[3], a[4]), cb = g2_lapl_point(b[3], b[4]);
+    r[1] = make_float4(ca.D, cb.D, ca.g4, cb.g4);
+    r[2 % NREC] = make_float4(ca.m, cb.m, ca.k3, cb.k3);
+    r[3 % NREC] = make_float4(ca.k4, cb.k4, 0.f, 0.f);
   } else {
     r[1] = make_float4(a[0], b[0], 0.f, 0.f);
   }
@@ -343,10 +345,11 @@ g2k1_bwd_sparse_kernel(int N2, int nsub, int sub_per_chunk, const float4* __rest
           g2_bwd_pair(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), f2(C.z, C.w), f2(D.x, D.y), nc[q],
                       nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q], acc[q]);
       } else if (MODE == BWD_LAPL) {
-        const float4 C = my[NREC * p + 2 % NREC];
+        const float4 C = my[NREC * p + 2 % NREC], D = my[NREC * p + 3 % NREC];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
-          g2_bwd_pair_lapl(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), nc[q], nd[q], rp[q], acc[q]);
+          g2_bwd_pair_lapl(x2, y2, f2(B.x, B.y), f2(B.z, B.w), f2(C.x, C.y), f2(C.z, C.w), f2(D.x, D.y),
+                           nc[q], nd[q], rp[q], acc[q]);
       } else {
 #pragma unroll
         for (int q = 0; q < Q; ++q) g2_bwd_pair_u(x2, y2, f2(B.x, B.y), nc[q], nd[q], rp[q], acc[q]);

@@ -72,8 +72,10 @@ void hc_g2_bwd_mode(int mode, int N, int M, const float* x, const float* y, cons
       bool v = i1 < N;
       float2 x2 = f2(x[i0], v ? x[i1] : x[i0]), y2 = f2(y[i0], v ? y[i1] : y[i0]);
       if (mode == 1) {
-        float2 g3 = f2(g[i0], v ? g[i1] : 0.f), g4 = f2(g[(size_t)N + i0], v ? g[(size_t)N + i1] : 0.f);
-        g2_bwd_pair_lapl(x2, y2, g3, g4, f2(g3.x + g4.x, g3.y + g4.y), f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), acc);
+        const G2LaplPoint ca = g2_lapl_point(g[i0], g[(size_t)N + i0]);
+        const G2LaplPoint cb = v ? g2_lapl_point(g[i1], g[(size_t)N + i1]) : g2_lapl_point(0.f, 0.f);
+        g2_bwd_pair_lapl(x2, y2, f2(ca.D, cb.D), f2(ca.g4, cb.g4), f2(ca.m, cb.m), f2(ca.k3, cb.k3),
+                         f2(ca.k4, cb.k4), f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), acc);
       } else {
         g2_bwd_pair_u(x2, y2, f2(g[i0], v ? g[i1] : 0.f), f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), acc);
       }

@@ -13,7 +13,8 @@ from spinn_b200 import _cabi  # noqa: E402
 NAMES = ["FFMA a=a*m+d (shared regs)", "FFMA a=b*c+a (3 distinct regs)", "FFMA2 a=a*m+d (shared)",
          "FFMA2 a=b*c+a (3 distinct pairs)", "FFMA2 a=b*bcast+a", "FMUL2+FADD2", "FFMA a=a*m+imm",
          "half FFMA2 + half FFMA (distinct)", "FADD distinct", "FMUL distinct", "MUFU.EX2",
-         "(reserved)", "FFMA2 operands reused pairwise"]
+         "16 FFMA2 bcast (no MUFU)", "FFMA2 operands reused pairwise", "16 FFMA2 bcast + 2 MUFU.EX2",
+         "16 FFMA2 bcast + 4 MUFU.EX2"]
 
 
 def main():
