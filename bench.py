@@ -39,7 +39,7 @@ UNIT = "point-node evals/s"
 FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 25.0
 MUFU_PER_PAIR = 2.0
 SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
-NCU_DRAM_BYTES_BWD_STRUCTURED = None                            # set from profiles/r01f_ncu_full.txt
+NCU_DRAM_BYTES_BWD_STRUCTURED = 134.686976e6 + 6.896640e6      # profiles/r01f_ncu_full.txt
 
 
 def workload_name(kind, n_points, n_nodes):

@@ -74,7 +74,8 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
   }
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y + b[k].x + c[k].x + c[k].y;
+  for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y + b[k].x;
+  if (WHICH >= 11) s += c[0].x + c[0].y + c[1].x + c[1].y;     // keep the MUFU results live
   if (s == 123.456f) sink[0] = s;
 }
 

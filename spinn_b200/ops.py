@@ -285,20 +285,23 @@ class _Attach(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         vx, vy = ctx.saved_tensors
-        gx = g * vx
-        if gx.dim() > 1:
-            gx = gx.sum(-1)
-        gy = None
-        if ctx.has_y:
-            gy = g * vy
-            if gy.dim() > 1:
-                gy = gy.sum(-1)
+
+        def along(v):                # sum_k g * v; a derivative declared "not provided" reads as zero
+            if v is None:
+                return torch.zeros_like(g if g.dim() == 1 else g[..., 0])
+            t = g * v
+            return t.sum(-1) if t.dim() > 1 else t
+
+        gx = along(vx)
+        gy = along(vy) if ctx.has_y else None
         return g, gx, gy, None, None
 
 
 def attach_tower_2d(x, y, u, ux, uy, uxx, uyy, uxy):
     """(N,K) jets -> u' such that the reference's ``_compute_derivatives``
-    (code/pde2d_base.py:46-62) recovers ux, uy, uxx, uyy (and uxy) from it."""
+    (code/pde2d_base.py:46-62) recovers ux, uy, uxx, uyy (and uxy) from it.
+    ``uxy=None``: the mixed derivative was not evaluated; the slots the recipe computes and drops
+    (d ux/dy, d uy/dx) read as zero."""
     ux_ = _Attach.apply(ux, x, y, uxx, uxy)
     uy_ = _Attach.apply(uy, x, y, uxy, uyy)
     return _Attach.apply(u, x, y, ux_, uy_)

@@ -6,6 +6,10 @@ from . import derivs
 
 
 class IBVP2D(PDE):
+    #: `_compute_derivatives` keeps u_xx = d(u_x)/dx and u_yy = d(u_y)/dy only (as the reference's
+    #: recipe): SPINN2D may skip the mixed derivative u_xy
+    needs_mixed_derivative = False
+
     FLAGS = (
         (("--nodes", "-n"), "nodes", 25, int, "Number of nodes to use."),
         (("--samples", "-s"), "samples", 100, int, "Number of sample points to use."),

@@ -34,6 +34,10 @@ def read_points(spec):
 
 
 class Poisson2D(PDE):
+    #: `_compute_derivatives` keeps u_xx = d(u_x)/dx and u_yy = d(u_y)/dy only (as the reference's
+    #: recipe): SPINN2D may skip the mixed derivative u_xy
+    needs_mixed_derivative = False
+
     FLAGS = (
         (("--f_nodes_int", "-ni"), "f_nodes_int", "npz:interior_nodes", str, "File containing interior nodes."),
         (("--f_nodes_bdy", "-nb"), "f_nodes_bdy", "npz:boundary_nodes", str, "File containing boundary nodes."),

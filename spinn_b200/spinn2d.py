@@ -103,7 +103,10 @@ class SPINN2D(nn.Module):
     #: affects how much is skipped, never the result)
     perm_refresh = 64
     #: also produce u_xy so that ``ag.grad(u_x, (x, y))`` is complete (the reference
-    #: computes it and drops it, pde2d_base.py:52-62); costs ~2 of 16 FP32 ops per pair
+    #: computes it and drops it, pde2d_base.py:52-62); costs 2 of 16 FP32 ops per pair.  Problem
+    #: classes whose derivative recipe provably drops the mixed term say so with the class
+    #: attribute ``needs_mixed_derivative = False`` (spinn_b200.problems.*); anything else --
+    #: e.g. the reference's own classes through dropin/ -- gets the complete tower.
     mixed_derivative = True
 
     @classmethod
@@ -122,6 +125,7 @@ class SPINN2D(nn.Module):
         self.activation = activation
         self.kind = kernel_kind(activation)
         self.use_pu = use_pu
+        self.mixed_derivative = bool(getattr(pde, "needs_mixed_derivative", True))
         self.layer1 = Shift2D(pde.nodes(), pde.fixed_nodes(), fixed_h=fixed_h)
         self.layer2 = nn.Linear(self.layer1.n, pde.n_vars(), bias=not use_pu)
         self.layer2.weight.data.fill_(0.0)
@@ -167,7 +171,7 @@ class SPINN2D(nn.Module):
             u, ux, uy, uxx, uyy, uxy = self.jets(x, y, level=3)
         else:
             u, ux, uy, uxx, uyy = self.jets(x, y, level=2)
-            uxy = torch.zeros_like(ux)
+            uxy = None
         return ops.attach_tower_2d(x, y, u, ux, uy, uxx, uyy, uxy).squeeze()
 
     def centers(self):

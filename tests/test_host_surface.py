@@ -99,6 +99,28 @@ def test_mixed_derivative_is_served(oracle_backend):
     assert maxnorm_err(uyx.detach().numpy(), c["jets_f64"][5, :, 0]) < 5e-6
 
 
+def test_mixed_derivative_is_skipped_only_for_problem_classes_that_drop_it(oracle_backend):
+    """Our problem mirrors declare that their recipe drops u_xy (as the reference's does,
+    pde2d_base.py:52-62): the forward then asks for 5 jets, and the dropped slots read as zero.
+    Any other problem class (e.g. the reference's own, through dropin/) gets the complete tower."""
+    levels = []
+    real = oracle_backend.forward
+    oracle_backend.forward = lambda dim, kind, level, *a, **k: (levels.append(level), real(dim, kind, level, *a, **k))[1]
+    pde = poisson2d_sine.Poisson2D(16, 36)
+    assert pde.needs_mixed_derivative is False
+    nn = spinn2d.SPINN2D(pde, spinn2d.gaussian)
+    with torch.no_grad():
+        nn.layer2.weight.normal_(0.0, 0.3)
+    xs, ys = pde.interior()
+    u = nn(xs, ys)
+    ux, uy = derivs.grad_xy(u, xs, ys)
+    uxx, uxy = derivs.grad_xy(ux, xs, ys)
+    assert levels == [2] and float(uxy.abs().max()) == 0.0 and float(uxx.abs().max()) > 0.0
+    nn2 = spinn2d.SPINN2D(_StubPDE(pde.nodes(), pde.fixed_nodes(), 1), spinn2d.gaussian)
+    nn2(xs, ys)
+    assert levels == [2, 3]
+
+
 @pytest.mark.parametrize("name", ["g1d_k1", "s1d_k1", "g1d_k2", "s1d_nofixed"])
 def test_tower_1d_reproduces_reference_autograd(oracle_backend, name):
     c = load_case(name)
