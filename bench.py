@@ -442,30 +442,58 @@ def run_ours(args):
         for p_ in params:            # gradients allocated inside the captures stay with the graphs
             p_.grad = None
 
-    # ---- one full optimisation step through the plug-in surface (1 GPU only): interior (all
-    # local points) + boundary loss + backward + Adam + the per-step loss.item() sync, exactly
-    # Optimizer.closure / opt.step of common.py ----
+    # ---- one full optimisation step through the plug-in surface: interior (this rank's points) +
+    # boundary loss + backward + (N > 1: one packed gradient all-reduce) + Adam + the per-step
+    # loss.item() sync, exactly Optimizer.closure / opt.step of common.py (N > 1: the
+    # data-parallel twin, spinn_b200/dist_optimizer.py) ----
     train_step = None
-    if ws == 1 and not args.no_e2e:
+    if not args.no_e2e:
         from spinn_b200.common import Optimizer
+        from spinn_b200.dist_optimizer import DistributedOptimizer
         from spinn_b200.spinn2d import Plotter2D
         prev_w = [p_.detach().clone() for p_ in params]
-        solver = Optimizer(pde, nn, Plotter2D(pde, nn), n_train=1, n_skip=10 ** 9, lr=1e-3, plot=False)
+        cls = Optimizer if ws == 1 else DistributedOptimizer       # the latter shards pde.p_samples
+        solver = cls(pde, nn, Plotter2D(pde, nn), n_train=1, n_skip=10 ** 9, lr=1e-3, plot=False)
         solver.opt = torch.optim.Adam(nn.parameters(), lr=1e-3)
         for _ in range(2):
             solver.opt.step(solver.closure)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         nts = max(3, args.steps // 2)
         for _ in range(nts):
             solver.opt.step(solver.closure)
         torch.cuda.synchronize()
-        train_step = {"ms": 1e3 * (time.perf_counter() - t0) / nts, "steps": nts,
-                      "what": "opt.step(closure): interior %d pts + boundary %d pts + backward + Adam + "
-                              "loss.item(), points resident on the GPU" % (N, pde.b_samples[0].numel())}
+        ms_ts = max_over_ranks(1e3 * (time.perf_counter() - t0) / nts)
+        train_step = {"ms": ms_ts, "steps": nts, "steps_per_s": 1e3 / ms_ts,
+                      "what": "opt.step(closure): interior %d pts (%d per GPU) + boundary %d pts + backward + "
+                              "%sAdam + loss.item(), points resident on the GPU"
+                              % (N, n_loc, pde.b_samples[0].numel(), "gradient all-reduce + " if ws > 1 else "")}
         with torch.no_grad():
             for p_, w_ in zip(params, prev_w):
                 p_.copy_(w_)
+        # the same loop with --graph: one captured step (incl. Adam and, for N > 1, the NCCL
+        # all-reduce) replayed; losses stay on the device until the end of solve()
+        import contextlib
+        import io
+        from spinn_b200.common import Plotter
+        from spinn_b200.graphed import GraphedOptimizer
+        gsolver = GraphedOptimizer(pde, nn, Plotter(pde, nn), n_train=4, n_skip=10 ** 9, tol=-1.0, lr=1e-3,
+                                   plot=False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gsolver.solve()                                           # 3 eager steps + capture + 1 replay
+            gsolver.n_train = nts
+            barrier()
+            t0 = time.perf_counter()
+            gsolver.solve()
+            torch.cuda.synchronize()
+        ms_g = max_over_ranks(1e3 * (time.perf_counter() - t0) / nts)
+        train_step["graphed_ms"] = ms_g
+        train_step["graphed_steps_per_s"] = 1e3 / ms_g
+        with torch.no_grad():
+            for p_, w_ in zip(params, prev_w):
+                p_.copy_(w_)
+        for p_ in params:
+            p_.grad = None
 
     if rank != 0:
         if ws > 1:

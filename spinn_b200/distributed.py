@@ -103,6 +103,8 @@ def shard_interior(pde, rank=None, world_size=None):
         rank, world_size, _ = world()
     if world_size == 1:
         return pde
+    if getattr(pde, "_shard", (None, None))[:2] == (rank, world_size):
+        return pde                                     # already holds this rank's slice
     for attr in ("p_samples", "interior_samples", "xs"):
         if hasattr(pde, attr):
             break
