@@ -541,6 +541,14 @@ def run_ours(args):
         "hbm": {"achieved_gbs": hbm_bytes_step / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": hbm_bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
         "microbench_lane_ops_per_s": peaks,
+        # FP32-pipe instruction slots: per pair the kernels issue 14 (fwd) / 16 (structured bwd) /
+        # 32 (general bwd) FP32 instructions; lanes x clock = 148 SM x 128 x 1.965 GHz.  (flop-based
+        # `frac` is lower because adds/multiplies count 1 flop and FMAs 2 for the same slot.)
+        "fp32_issue_slots": {
+            "instr_per_pair": {"fwd": 14, "bwd": 32 if args.general_backward else 16},
+            "fwd_frac_of_lane_rate": pairs_loc * 14 / (ms_fwd * 1e-3) / (nominal_fp32 / 2),
+            "bwd_frac_of_lane_rate": pairs_loc * (32 if args.general_backward else 16) / (ms_bwd * 1e-3) / (nominal_fp32 / 2),
+            "probe_same_mix_frac": "0.775 (16 warps/SM) .. 0.824 (64 warps/SM), profiles/r01_microbench_probes.txt"},
     }
 
     # the general 5-row backward on the same inputs (what a residual using all jets would cost)
