@@ -1,5 +1,5 @@
-"""Inviscid 1-D Burgers equation by FD-SPINN time stepping (mirrors
-/root/reference/code/burgers1d_fd_spinn.py).
+"""Inviscid 1-D Burgers equation u_t + u u_x = 0, u(0)=u(1)=0, by FD-SPINN time stepping
+(problem of /root/reference/code/burgers1d_fd_spinn.py; no exact solution).
 
     python -m spinn_b200.problems.burgers1d_fd_spinn --gpu [--graph]
 """
@@ -14,18 +14,11 @@ class Burgers1D(FDSPINN1D):
     def initial(self, x):
         return torch.sin(2.0 * np.pi * x)
 
-    def pde(self, x, u, ux, uxx, u0, dt):
-        return -dt * u * ux - u + u0
-
     def has_exact(self):
         return False
 
-    def boundary_loss(self, nn):
-        bc = nn(self.boundary()) - 0.0
-        return 100 * (bc ** 2).sum()
-
-    def plot_points(self):
-        return np.linspace(0.0, 1.0, min(2 * self.ns, 500))
+    def pde(self, x, u, ux, uxx, u0, dt):
+        return -dt * u * ux - u + u0
 
 
 DEFAULTS = dict(nodes=40, samples=400, dt=0.01, tol=5e-6, lr=1e-4, n_train=5000, n_skip=500)

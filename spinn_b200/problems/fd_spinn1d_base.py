@@ -89,11 +89,23 @@ class FDSPINN1D(BasicODE):
         super().setup_argparse(parser, **kw)
         add_flags(parser, cls.FD_FLAGS, kw)
 
+    #: homogeneous Dirichlet penalty used by all three reference drivers: w * sum(u(boundary)^2)
+    boundary_penalty = 100
+    #: number of plot/error points as a function of the sample count
+    n_plot = staticmethod(lambda ns: min(2 * ns, 500))
+
     def __init__(self, n, ns, sample_frac=1.0, dt=1e-3, T=1.0, t_skip=10):
-        super().__init__(n, ns, sample_frac)
+        super().__init__(n, ns, sample_frac)          # geometry on `domain` (ode_base.BasicODE)
         self.iter, self.t = 0, 0.0
         self.dt, self.T, self.t_skip = dt, T, t_skip
         self.u0 = self.initial(self.xs)
+
+    def boundary_loss(self, nn):
+        return self.boundary_penalty * (nn(self.boundary()) ** 2).sum()
+
+    def plot_points(self):
+        lo, hi = self.domain
+        return np.linspace(lo, hi, self.n_plot(self.ns))
 
     def initial(self, x):
         return torch.zeros_like(x).to(device())
@@ -107,7 +119,7 @@ class FDSPINN1D(BasicODE):
         self.u0 = self.initial(self.xs)
 
     def sample_arrays(self, *arrays):
-        if abs(self.sample_frac - 1.0) < 1e-3:
+        if self.uses_all_samples():
             return arrays
         idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
         return tuple(a[idx] for a in arrays)

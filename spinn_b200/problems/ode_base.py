@@ -1,8 +1,17 @@
-"""1-D problem base (mirrors /root/reference/code/ode_base.py:8-92)."""
+"""1-D problem base: uniform interior nodes/samples on an interval, Dirichlet end points
+(behaviour of /root/reference/code/ode_base.py:8-92; FD-SPINN re-uses it on other intervals)."""
 import numpy as np
 
 from ..common import PDE, add_flags, tensor
 from . import derivs
+
+
+def interior_grid(count, lo=0.0, hi=1.0):
+    """The `count` interior points of the uniform grid with count+2 points on [lo, hi]
+    (ode_base.py:49: i/(n+1) on the unit interval; advection1d_fd_spinn.py:15-20 on (-1, 1))."""
+    if (lo, hi) == (0.0, 1.0):
+        return np.arange(1, count + 1) / (count + 1)
+    return np.asarray([lo + (hi - lo) * i / (count + 1) for i in range(1, count + 1)])
 
 
 class BasicODE(PDE):
@@ -11,51 +20,57 @@ class BasicODE(PDE):
         (("--samples", "-s"), "samples", 30, int, "Number of sample points to use."),
         (("--sample-frac", "-f"), "sample_frac", 1.0, float, "Fraction of interior nodes used for sampling."),
     )
-
-    @classmethod
-    def from_args(cls, args):
-        return cls(args.nodes, args.samples, args.sample_frac)
+    domain = (0.0, 1.0)
 
     @classmethod
     def setup_argparse(cls, parser, **kw):
         add_flags(parser, cls.FLAGS, kw)
 
-    def _compute_derivatives(self, u, x):
-        return derivs.jets_1d(u, x)
+    @classmethod
+    def from_args(cls, args):
+        return cls(args.nodes, args.samples, args.sample_frac)
 
     def __init__(self, n, ns, sample_frac=1.0):
+        lo, hi = self.domain
         self.n, self.ns, self.sample_frac = n, ns, sample_frac
-        self.xn = np.arange(1, n + 1) / (n + 1)                       # ode_base.py:49
-        self.xs = tensor(np.arange(1, ns + 1) / (ns + 1), requires_grad=True)
-        self.xbn = np.array([0.0, 1.0])
+        self.xn = interior_grid(n, lo, hi)                            # free node centres
+        self.xs = tensor(interior_grid(ns, lo, hi), requires_grad=True)   # collocation points
+        self.xbn = np.array([lo, hi])                                 # fixed nodes = boundary points
         self.xb = tensor(self.xbn)
-        self.rng_interior = np.arange(self.ns)
-        self.sample_size = int(self.sample_frac * self.ns)
+        self.rng_interior = np.arange(ns)
+        self.sample_size = int(sample_frac * ns)
 
+    # geometry handed to the network / plotter
     def nodes(self):
         return self.xn
 
     def fixed_nodes(self):
         return self.xbn
 
-    def interior(self):
-        if abs(self.sample_frac - 1.0) < 1e-3:
-            return self.xs
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        return self.xs[idx]
-
     def boundary(self):
         return self.xb
 
     def plot_points(self):
-        return np.linspace(0.0, 1.0, 2 * self.ns)
+        lo, hi = self.domain
+        return np.linspace(lo, hi, 2 * self.ns)
+
+    def uses_all_samples(self):
+        return abs(self.sample_frac - 1.0) < 1e-3
+
+    def interior(self):
+        if self.uses_all_samples():
+            return self.xs
+        # unseeded global NumPy stream, one draw per call (ode_base.py:64-68)
+        pick = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
+        return self.xs[pick]
+
+    # physics
+    def _compute_derivatives(self, u, x):
+        return derivs.jets_1d(u, x)
 
     def _get_residue(self, nn):
-        xs = self.interior()
-        u = nn(xs)
-        u, ux, uxx = self._compute_derivatives(u, xs)
-        return self.pde(xs, u, ux, uxx)
+        x = self.interior()
+        return self.pde(*((x,) + self._compute_derivatives(nn(x), x)))
 
     def interior_loss(self, nn):
-        res = self._get_residue(nn)
-        return (res ** 2).mean()
+        return (self._get_residue(nn) ** 2).mean()
