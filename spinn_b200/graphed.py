@@ -27,6 +27,7 @@ class GraphedOptimizer(DistributedOptimizer):
     packed gradient all-reduce (NCCL) is captured inside the graph as well."""
 
     WARMUP_STEPS = 3          # eager steps before capture (they are real training steps)
+    FUSED_ADAM = True
 
     def _body(self):
         loss = self._local_loss()
@@ -55,7 +56,9 @@ class GraphedOptimizer(DistributedOptimizer):
         if dev.type != "cuda":
             raise RuntimeError("--graph needs --gpu")
         if self.opt is None:
-            self.opt = torch.optim.Adam(params, lr=self.lr, capturable=True)
+            # one multi-tensor kernel for the whole update (same arithmetic as the default
+            # implementation; SURVEY.md 8f-1 "fused Adam")
+            self.opt = torch.optim.Adam(params, lr=self.lr, capturable=True, fused=self.FUSED_ADAM)
         if hasattr(self.pde, "enable_static_sampling"):
             self.pde.enable_static_sampling()
         n_train = self.n_train

@@ -82,6 +82,11 @@ def fd_run(steps):
             "--gpu", "--n-train", str(steps), "--n-skip", str(10 ** 9)]
     res = {}
     dense = AppFD1D(pde_cls=fd.Heat1D, nn_cls=torch_port.DenseSPINN1D, plotter_cls=fd.FDPlotter1D)
+    mk_dense = lambda: AppFD1D(pde_cls=fd.Heat1D, nn_cls=torch_port.DenseSPINN1D, plotter_cls=fd.FDPlotter1D)
+    with contextlib.redirect_stdout(io.StringIO()):          # one-time costs (module loads) out of the way
+        for mk, extra in ((fd.make_app, []), (fd.make_app, ["--graph"]), (mk_dense, [])):
+            mk().run(args=["--nodes", "10", "--samples", "100", "--dt", "0.01", "-T", "0.02", "--tol", "1e-30",
+                           "--gpu", "--n-train", "5"] + extra)
     for tag, app, extra in (("fused", fd.make_app(), []), ("fused_graphed", fd.make_app(), ["--graph"]),
                             ("dense_eager_same_gpu", dense, [])):
         np.random.seed(0)
