@@ -99,8 +99,11 @@ SP_HD float2 f2ex2neg(float2 t) { return make_float2(ex2f_fast(-t.x), ex2f_fast(
 // =============================================================================
 // FAST PATH: 2-D Gaussian, one output (K=1).  Two lanes of a float2 carry two
 // NODES in the forward pass (points live in registers, node records stream from
-// shared memory) and two POINTS in the backward pass (nodes live in registers,
-// point records stream from shared memory).
+// shared memory).  In the backward pass nodes live in registers and point records
+// stream from shared memory; the lanes are the two POINTS of a record in the general
+// mode and two adjacent NODES in the structured modes (g2k1_bwd_kernel).  The pair
+// functions below do not care: whichever operands the caller builds with f2dup()
+// become scalar-broadcast operands of the packed instructions.
 // =============================================================================
 
 // Per-node derived parameters for the forward pass (built once per launch by the
