@@ -286,6 +286,42 @@ def test_full_size_point_sharding_is_additive(full_state):
     assert float((acc - whole).abs().max() / scale) < 5e-6
 
 
+def test_beyond_baseline_size_16m_points_16384_nodes():
+    """4x the points and 4x the nodes of the BASELINE workload (2.7e11 pairs; the node table no
+    longer fits one shared-memory tile, point-record offsets pass 2^31 bytes): sampled forward
+    points and sampled backward nodes against the fp64 oracle, bit-exact repeatability."""
+    from spinn_b200 import synthetic
+    from spinn_b200.fused_step import PoissonInteriorStep
+    pde, nn = synthetic.make_state(nodes=124 * 124, b_nodes=252, samples=4096 * 4096, device="cuda")
+    xs, ys = (t.detach() for t in pde.p_samples)
+    N = xs.numel()
+    assert N == 16777216 and nn.layer2.weight.shape == (1, 16384)
+    l1, l2 = nn.layer1, nn.layer2
+    xc, yc = (t.detach().cpu().numpy() for t in l1.centers())
+    h, W, b = (t.detach().cpu().numpy() for t in (l1.h, l2.weight, l2.bias))
+    with torch.no_grad():
+        jets = torch.stack(nn.jets(xs, ys, level=2)).squeeze(-1)
+    idx = torch.cat((torch.tensor([0, 1, N - 2, N - 1]),
+                     torch.randint(0, N, (60,), generator=torch.Generator().manual_seed(3)))).cuda()
+    ref = cf.jets2d("gaussian", xs[idx].cpu().numpy(), ys[idx].cpu().numpy(), xc, yc, h, W, b)[:5, :, 0]
+    got = jets[:, idx].cpu().numpy()
+    for a in range(5):
+        assert mixed_err(got[a], ref[a]) < TOL, (a, mixed_err(got[a], ref[a]))
+    del jets
+    step = PoissonInteriorStep(nn, xs, ys)
+    flat = step.run(all_reduce=False).clone()
+    g = step.gjets.cpu().numpy().astype(np.float64)[:, :, None]
+    nodes = np.array([0, 15375, 15376, 16383])
+    G = cf.grads2d("gaussian", xs.cpu().numpy(), ys.cpu().numpy(), xc[nodes], yc[nodes], h[nodes], W[:, nodes], g,
+                   chunk=262144)
+    p = step.pack
+    for name, key, sel in (("d_W", "d_W", nodes), ("d_h", "d_h", nodes), ("d_x", "d_xc", nodes[:2])):
+        got = p.view(name).cpu().numpy()
+        want = np.asarray(G[key]).reshape(-1)[:len(sel)]
+        assert np.max(np.abs(got[sel] - want)) < 1e-5 * np.abs(got).max() + 1e-5 * np.abs(want).max(), name
+    assert torch.equal(flat, step.run(all_reduce=False))
+
+
 @pytest.mark.parametrize("mask", [0x18, 0x08, 0x10, 0x01, 0x19, 0x06, 0x1F])
 @pytest.mark.parametrize("kind,K", [("gaussian", 1), ("gaussian", 3), ("softplus", 1)])
 def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
