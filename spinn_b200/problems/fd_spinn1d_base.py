@@ -119,10 +119,7 @@ class FDSPINN1D(BasicODE):
         self.u0 = self.initial(self.xs)
 
     def sample_arrays(self, *arrays):
-        if self.uses_all_samples():
-            return arrays
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        return tuple(a[idx] for a in arrays)
+        return self.pick(*arrays)                # the same draw for the points and for u0
 
     def interior(self):
         return self.xs
@@ -136,8 +133,7 @@ class FDSPINN1D(BasicODE):
 
     # -- CUDA-graph support (spinn_b200/graphed.py); not in the reference ------------------
     def enable_static_sampling(self):
-        if abs(self.sample_frac - 1.0) >= 1e-3:
-            raise NotImplementedError("--graph with --sample-frac < 1 is not available for FD-SPINN")
+        super().enable_static_sampling()
         if not getattr(self, "_u0_static", False):
             # one buffer for the previous-level field, detached from whatever produced it
             self.u0 = self.u0.detach().clone()

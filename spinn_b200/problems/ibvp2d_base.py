@@ -3,9 +3,10 @@ import numpy as np
 
 from ..common import PDE, add_flags, tensor
 from . import derivs
+from .sampling import SubSampling
 
 
-class IBVP2D(PDE):
+class IBVP2D(SubSampling, PDE):
     #: `_compute_derivatives` keeps u_xx = d(u_x)/dx and u_yy = d(u_y)/dy only (as the reference's
     #: recipe): SPINN2D may skip the mixed derivative u_xy
     needs_mixed_derivative = False
@@ -82,11 +83,10 @@ class IBVP2D(PDE):
         return self.f_nodes
 
     def interior(self):
-        if abs(self.sample_frac - 1.0) < 1e-3:
-            return self.p_samples
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        x, t = self.p_samples
-        return x[idx], t[idx]
+        return self.pick(*self.p_samples)
+
+    def _sampling_device(self):
+        return self.p_samples[0].device
 
     def boundary(self):
         return self.b_samples

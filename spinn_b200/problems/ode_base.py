@@ -4,6 +4,7 @@ import numpy as np
 
 from ..common import PDE, add_flags, tensor
 from . import derivs
+from .sampling import SubSampling
 
 
 def interior_grid(count, lo=0.0, hi=1.0):
@@ -14,7 +15,7 @@ def interior_grid(count, lo=0.0, hi=1.0):
     return np.asarray([lo + (hi - lo) * i / (count + 1) for i in range(1, count + 1)])
 
 
-class BasicODE(PDE):
+class BasicODE(SubSampling, PDE):
     FLAGS = (
         (("--nodes", "-n"), "nodes", 10, int, "Number of nodes to use."),
         (("--samples", "-s"), "samples", 30, int, "Number of sample points to use."),
@@ -54,15 +55,12 @@ class BasicODE(PDE):
         lo, hi = self.domain
         return np.linspace(lo, hi, 2 * self.ns)
 
-    def uses_all_samples(self):
-        return abs(self.sample_frac - 1.0) < 1e-3
-
     def interior(self):
-        if self.uses_all_samples():
-            return self.xs
-        # unseeded global NumPy stream, one draw per call (ode_base.py:64-68)
-        pick = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        return self.xs[pick]
+        # one draw from the unseeded global NumPy stream per call (ode_base.py:64-68)
+        return self.pick(self.xs)[0]
+
+    def _sampling_device(self):
+        return self.xs.device
 
     # physics
     def _compute_derivatives(self, u, x):

@@ -3,6 +3,7 @@ import numpy as np
 
 from ..common import PDE, add_flags, tensor
 from . import derivs
+from .sampling import SubSampling
 
 
 def _cell_centres(n, half):
@@ -20,7 +21,7 @@ def _side(count):
     return round(np.sqrt(count) + 0.49)
 
 
-class RegularPDE(PDE):
+class RegularPDE(SubSampling, PDE):
     #: `_compute_derivatives` keeps u_xx = d(u_x)/dx and u_yy = d(u_y)/dy only (as the reference's
     #: recipe): SPINN2D may skip the mixed derivative u_xy
     needs_mixed_derivative = False
@@ -76,41 +77,10 @@ class RegularPDE(PDE):
         return self.f_nodes
 
     def interior(self):
-        if abs(self.sample_frac - 1.0) < 1e-3:
-            return self.p_samples
-        x, y = self.p_samples
-        if getattr(self, "_idx_dev", None) is not None:      # CUDA-graph mode: static index buffer
-            return x[self._idx_dev], y[self._idx_dev]
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        return x[idx], y[idx]
+        return self.pick(*self.p_samples)
 
-    # -- CUDA-graph support (spinn_b200/graphed.py); not in the reference ------------------
-    def enable_static_sampling(self):
-        """Route the random sub-sample through a fixed device buffer that is refilled from the
-        SAME np.random.choice stream before every step (graph_pre_step)."""
-        if abs(self.sample_frac - 1.0) < 1e-3 or getattr(self, "_idx_dev", None) is not None:
-            return
-        import torch
-        dev = self.p_samples[0].device
-        # ring of pinned staging buffers: the host runs ahead of the GPU in graph mode, so a
-        # buffer may only be rewritten once the copy that read it has completed
-        self._idx_ring = [(torch.empty(self.sample_size, dtype=torch.int64).pin_memory(), torch.cuda.Event())
-                          for _ in range(4)]
-        self._idx_turn = 0
-        self._idx_dev = torch.zeros(self.sample_size, dtype=torch.int64, device=dev)
-
-    def graph_pre_step(self):
-        if getattr(self, "_idx_dev", None) is None:
-            return
-        import torch
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        host, ev = self._idx_ring[self._idx_turn % len(self._idx_ring)]
-        if self._idx_turn >= len(self._idx_ring):
-            ev.synchronize()
-        self._idx_turn += 1
-        host.copy_(torch.from_numpy(idx))
-        self._idx_dev.copy_(host, non_blocking=True)
-        ev.record()
+    def _sampling_device(self):
+        return self.p_samples[0].device
 
     def boundary(self):
         return self.b_samples

@@ -15,6 +15,7 @@ import numpy as np
 from ..common import PDE, add_flags, tensor
 from ..spinn2d import App2D, Plotter2D, SPINN2D
 from . import derivs
+from .sampling import SubSampling
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mesh_data.npz")
 _KEYS = {"f_nodes_int": "interior_nodes", "f_nodes_bdy": "boundary_nodes",
@@ -33,7 +34,7 @@ def read_points(spec):
     return pts[:, 0], pts[:, 1]
 
 
-class Poisson2D(PDE):
+class Poisson2D(SubSampling, PDE):
     #: `_compute_derivatives` keeps u_xx = d(u_x)/dx and u_yy = d(u_y)/dy only (as the reference's
     #: recipe): SPINN2D may skip the mixed derivative u_xy
     needs_mixed_derivative = False
@@ -79,11 +80,10 @@ class Poisson2D(PDE):
         return self.boundary_nodes
 
     def interior(self):
-        if abs(self.sample_frac - 1.0) < 1e-3:
-            return self.interior_samples
-        idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
-        x, y = self.interior_samples
-        return x[idx], y[idx]
+        return self.pick(*self.interior_samples)
+
+    def _sampling_device(self):
+        return self.interior_samples[0].device
 
     def boundary(self):
         return self.boundary_samples

@@ -118,15 +118,12 @@ def test_config_trajectory_on_gpu_matches_reference(name, modname):
                                           ("advection1d_fd", "advection1d_fd_spinn")])
 def test_fd_spinn_time_stepping_on_gpu_matches_reference(name, modname, graph):
     """FD-SPINN outer loop (reference fd_spinn1d_base.py:142-190) on the 1-D fused op: eager, and
-    with ONE captured training step replayed across all time levels (--graph)."""
+    with ONE captured training step replayed across all time levels (--graph; the advection case
+    sub-samples half of the points per step through the static index buffer)."""
     import importlib
     mod = importlib.import_module(f"spinn_b200.problems.{modname}")
     d = np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
     args = [str(a) for a in d["args"]]
-    if graph and "--sample-frac" in args:
-        with pytest.raises(NotImplementedError):
-            mod.make_app().run(args=args + ["--gpu", "--graph"])
-        return
     np.random.seed(0)
     torch.manual_seed(0)
     app = mod.make_app()
@@ -223,3 +220,27 @@ def test_cutoff_and_graph_together_follow_the_reference_trajectory():
     loss = np.asarray(app.solver.loss)
     rel = np.abs(loss - ref[:120]) / np.abs(ref[:120])
     assert rel[:10].max() < 5e-5 and rel.max() < 3e-3, rel.max()
+
+
+@pytest.mark.parametrize("modname,args", [
+    ("ode3", ["--nodes", "5", "--samples", "60", "--sample-frac", "0.5", "--lr", "1e-3", "--tol", "1e-30",
+              "--n-train", "60"]),
+    ("heat1d", ["--nodes", "50", "--samples", "200", "--sample-frac", "0.5", "--lr", "1e-2", "--n-train", "40"]),
+    ("poisson2d_irreg_dom", ["--sample-frac", "0.25", "--lr", "1e-3", "--n-train", "30"])])
+def test_subsampling_under_graph_replays_the_eager_draws(modname, args):
+    """`--sample-frac < 1` with `--graph`: every replay gathers through the static index buffer that
+    is refilled from the SAME np.random stream the eager loop consumes (one draw per step), for all
+    problem bases (BasicODE, IBVP2D, irregular-domain Poisson2D; RegularPDE is covered by the cavity)."""
+    import importlib
+    mod = importlib.import_module(f"spinn_b200.problems.{modname}")
+    losses = []
+    for extra in ([], ["--graph"]):
+        np.random.seed(0)
+        torch.manual_seed(0)
+        app = mod.make_app()
+        app.run(args=args + ["--gpu"] + extra)
+        losses.append(np.asarray(app.solver.loss))
+    eager, graphed = losses
+    assert len(eager) == len(graphed)
+    rel = np.abs(eager - graphed) / np.abs(eager)
+    assert rel[:10].max() < 5e-5 and rel.max() < 3e-3, (modname, rel[:10].max(), rel.max())
