@@ -42,7 +42,7 @@ class FDPlotter1D(Plotter1D):
         diff = self._exact_at_next_level(xn) - pn
         return np.mean(np.abs(diff)), np.sqrt(np.mean(diff ** 2)), np.max(np.abs(diff))
 
-    def plot(self):
+    def plot_solution(self):
         import matplotlib.pyplot as plt
         xn, pn = self.get_plot_data()
         pde = self.pde

@@ -501,3 +501,50 @@ def test_tolerance_stop_takes_effect_one_iteration_late(oracle_backend):
     assert len(loss) == len(ref) == 441
     rel = np.abs(loss - ref) / np.abs(ref)
     assert rel.max() < 2e-3
+
+
+def test_live_plot_protocol_1d(oracle_backend, monkeypatch):
+    """`--plot`: Plotter1D.plot() = plot_solution() then plot_weights() (both overridable, reference
+    spinn1d.py:44-83), FDPlotter1D overrides plot_solution only; exercised with a recording stand-in
+    for matplotlib (not installed here)."""
+    import types
+    calls = []
+
+    class Line:
+        def set_data(self, *a):
+            calls.append("set_data")
+
+    class Title:
+        def set_text(self, t):
+            calls.append("title")
+
+    canvas = types.SimpleNamespace(draw=lambda: calls.append("draw"), flush_events=lambda: calls.append("flush"))
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.plot = lambda *a, **k: (calls.append("plot"), [Line()])[1]
+    for n in ("grid", "xlim", "ylim", "legend", "pause", "show"):
+        setattr(plt, n, (lambda nn: (lambda *a, **k: calls.append(nn)))(n))
+    plt.gcf = lambda: types.SimpleNamespace(canvas=canvas)
+    plt.title = lambda *a, **k: Title()
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    from spinn_b200.problems import fd_spinn1d_base, heat1d_fd_spinn
+    pde = ode3.ODESimple(3, 20)
+    pl = spinn1d.Plotter1D(pde, spinn1d.SPINN1D(pde, spinn1d.gaussian))
+    e1, e2 = pl.plot(), pl.plot()
+    assert e1 == e2 == pl.get_error()
+    assert calls == ["plot", "plot", "grid", "xlim", "ylim", "plot", "legend", "pause",
+                     "set_data", "set_data", "draw", "flush"]
+    seen = []
+    pl.plot_weights = lambda: seen.append("weights")            # overriding hooks is honoured
+    pl.plot()
+    assert seen == ["weights"]
+    calls.clear()
+    pde = heat1d_fd_spinn.Heat1D(5, 20)
+    fpl = fd_spinn1d_base.FDPlotter1D(pde, spinn1d.SPINN1D(pde, spinn1d.gaussian))
+    t_before = pde.t
+    assert fpl.plot() == fpl.get_error() and pde.t == t_before   # exact solution taken at t + dt
+    assert "title" not in calls and calls.count("plot") == 3
+    fpl.plot()
+    assert "title" in calls
