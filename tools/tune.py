@@ -75,8 +75,9 @@ def main():
             ms = time_ms(bwd)
             n = step.pack.slices["loss"][0]
             err = float((step.pack.flat[:n] - ref[:n]).abs().max() / ref[:n].abs().max())
-            print(f"bwd variant {v} waves {w}: {ms:8.3f} ms   {N * M * 53 / ms / 1e9:7.2f} TFLOP/s   maxdiff {err:.2e}",
-                  flush=True)
+            flop = {0x18: 25, 0x08: 25, 0x10: 25, 0x01: 15}.get(a.mask, 53)    # per pair, by backward mode
+            print(f"bwd variant {v} waves {w}: {ms:8.3f} ms   {N * M * flop / ms / 1e9:7.2f} TFLOP/s "
+                  f"({flop} flop/pair)   maxdiff {err:.2e}", flush=True)
 
 
 if __name__ == "__main__":
