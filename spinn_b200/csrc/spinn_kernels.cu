@@ -184,14 +184,14 @@ __global__ void pack_points_g2bwd_kernel(int N, int N2, const float* __restrict_
   float a[5], b[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const bool need = (MODE == BWD_ALL) || (MODE == BWD_LAPL && k >= 3) || (MODE == BWD_U && k == 0);
+    const bool need = bwd_general(MODE) || (MODE == BWD_LAPL && k >= 3) || (MODE == BWD_U && k == 0);
     const bool have = need && ((mask >> k) & 1);
     a[k] = have ? g[k * n + i0] : 0.f;
     b[k] = (have && v1) ? g[k * n + i1] : 0.f;
   }
   float4* r = recs + (size_t)NREC * p;
   r[0] = make_float4(x0, x1, y0, y1);
-  if (MODE == BWD_ALL) {
+  if (bwd_general(MODE)) {
     r[1] = make_float4(a[0], b[0], a[1], b[1]);
     r[2] = make_float4(a[2], b[2], a[3], b[3]);
     r[3 % NREC] = make_float4(a[4], b[4], 0.f, 0.f);
@@ -407,7 +407,7 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
   // (5 of them in the (u_xx,u_yy) mode) are the scalar-broadcast operands -- an FFMA2 with three
   // full register-pair operands issues at half rate (tools/microbench.py probe 3), and this
   // assignment leaves only the three accumulate-products in that class.
-  constexpr bool LN = (MODE != BWD_ALL) && (Q % 2 == 0);
+  constexpr bool LN = (MODE == BWD_LAPL || MODE == BWD_U) && (Q % 2 == 0);
   constexpr int QS = LN ? Q / 2 : Q;             // instruction streams per thread
   // ring of point-record tiles filled by TMA bulk copies: tiles t+1.. are in flight while
   // tile t is consumed; `full[s]` flips when the bytes of stage s have landed
@@ -480,14 +480,19 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
     for (int p = 0; p < n; ++p) {
       const float4 A = sm4[NREC * p + 0], B = sm4[NREC * p + 1];
       const float2 x2 = f2(A.x, A.y), y2 = f2(A.z, A.w);
-      if (MODE == BWD_ALL) {
+      if (bwd_general(MODE)) {
         const float4 C = sm4[NREC * p + 2 % NREC], D = sm4[NREC * p + 3 % NREC];
         const float2 g0 = f2(B.x, B.y), g1 = f2(B.z, B.w), g2 = f2(C.x, C.y), g3 = f2(C.z, C.w);
         const float2 g4 = f2(D.x, D.y);
 #pragma unroll
-        for (int q = 0; q < QS; ++q)
-          g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q],
-                              k2p[q], acc[q]);
+        for (int q = 0; q < QS; ++q) {
+          if (MODE == BWD_ALL)
+            g2_bwd_pair(x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q],
+                                k2p[q], acc[q]);
+          else
+            g2_bwd_pair_mask<(MODE >= BWD_MASKED ? MODE - BWD_MASKED : 0x1F)>(
+                x2, y2, g0, g1, g2, g3, g4, nc[q], nd[q], rp[q], nrt[q], rho[q], nk1[q], k2p[q], acc[q]);
+        }
       } else if (MODE == BWD_LAPL) {
         const float4 C = sm4[NREC * p + 2 % NREC];
         const float2 k4 = *reinterpret_cast<const float2*>(&sm4[NREC * p + 3 % NREC]);
@@ -871,6 +876,9 @@ static int effective_mask(int dim, int level, int present_mask) {
 static int bwd_mode_for(int mask) {
   if (mask == 0x01) return BWD_U;
   if ((mask & ~0x18) == 0) return BWD_LAPL;
+  // residual patterns of the packaged space-time problems: advection (u_x,u_t), heat (u_t,u_xx),
+  // Burgers (u,u_x,u_t,u_xx)
+  if (mask == 0x06 || mask == 0x0C || mask == 0x0F) return BWD_MASKED + mask;
   return BWD_ALL;
 }
 
@@ -912,7 +920,7 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
     const int cand[5] = {2, 0, 1, 4, 5};
     const double cost[5] = {1.0, 1.015, 1.06, 1.10, 0.97};
     double best = 1e300;
-    for (int i = 0; i < (mode == BWD_ALL ? 4 : 5); ++i) {
+    for (int i = 0; i < ((mode == BWD_LAPL || mode == BWD_U) ? 5 : 4); ++i) {
       const BwdCfg c = BWD_CFGS[cand[i]];
       const double w = (double)round_up_i(M, c.q * c.threads) * cost[i];
       if (w < best) { best = w; p.variant = cand[i]; }
@@ -1156,7 +1164,7 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
     float4* ptrecs = (float4*)(base + p.off_pts);
     const int mode = bwd_mode_for(mask);
     const int pgrid = ceil_div_i(p.N2, 256);
-    if (mode == BWD_ALL) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    if (bwd_general(mode)) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     else if (mode == BWD_LAPL) pack_points_g2bwd_kernel<BWD_LAPL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     else pack_points_g2bwd_kernel<BWD_U><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     LAUNCH_CHECK("pack_points_g2bwd_kernel");
@@ -1166,6 +1174,12 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
       g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_ALL><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);  \
     else if (mode == BWD_LAPL)                                                                                \
       g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_LAPL><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else if (mode == BWD_MASKED + 0x06)                                                                       \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_MASKED + 0x06><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else if (mode == BWD_MASKED + 0x0C)                                                                       \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_MASKED + 0x0C><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else if (mode == BWD_MASKED + 0x0F)                                                                       \
+      g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_MASKED + 0x0F><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
     else                                                                                                      \
       g2k1_bwd_kernel<Q_, T_, B_, TILE_, BWD_U><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials);    \
   } while (0)

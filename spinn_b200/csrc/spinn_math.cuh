@@ -209,6 +209,64 @@ SP_HD void g2_bwd_pair(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, fl
   acc[3] = f2fma<PA>(E, nhh, acc[3]);
 }
 
+// The same algebra with the upstream rows that are structurally ABSENT (bit clear in MASK: autograd
+// handed None for that jet) removed at compile time -- e.g. u_t - c^2 u_xx (heat, IBVP2D) only has
+// g2, g3: 25 instead of 32 instructions.  MASK = 0x1F reproduces g2_bwd_pair instruction for
+// instruction.  fma_opt<HP, HC>(a, b, c) = a*b + c where the product / the addend may be absent.
+template <bool HP, bool HC, int PK>
+SP_HD float2 fma_opt(float2 a, float2 b, float2 c) {
+  if (HP && HC) return f2fma<PK>(a, b, c);
+  if (HP) return f2mul<PK>(a, b);
+  if (HC) return c;
+  return f2(0.f, 0.f);
+}
+template <int MASK, int PK = 1, int PA = 1>
+SP_HD void g2_bwd_pair_mask(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, float2 g3, float2 g4,
+                            float2 nc, float2 nd, float2 rp, float2 nrt, float2 rho, float2 nk1,
+                            float2 k2p, float2* acc) {
+  constexpr bool H0 = MASK & 1, H1 = MASK & 2, H2 = MASK & 4, H3 = MASK & 8, H4 = MASK & 16;
+  constexpr bool HQ = H3 || H4, HAB = H1 || H2, HBP = H0 || HQ;
+  const float2 nsig2 = f2dup(-SIG2_F), zero = f2(0.f, 0.f);
+  float2 X  = f2add<PK>(x2, nc);
+  float2 Y  = f2add<PK>(y2, nd);
+  float2 xi = f2mul<PK>(X, rp);
+  float2 et = f2mul<PK>(Y, rp);
+  float2 hx = f2fma<PK>(xi, xi, nsig2);
+  float2 hy = f2fma<PK>(et, et, nsig2);
+  float2 t  = f2add<PK>(hx, hy);
+  float2 E  = f2ex2neg(t);
+  float2 a  = H1 ? f2mul<PK>(g1, xi) : zero;
+  float2 b  = H2 ? f2mul<PK>(g2, et) : zero;
+  float2 q  = H3 ? f2mul<PK>(g3, hx) : zero;
+  q = fma_opt<H4, H3, PK>(g4, hy, q);
+  float2 bp = fma_opt<HQ, H0, PK>(rho, q, g0);
+  float2 ab = (H1 && H2) ? f2add<PK>(a, b) : (H1 ? a : b);
+  float2 PE = fma_opt<HAB, HBP, PK>(nrt, ab, bp);
+  // x
+  constexpr bool HBX = H2 || HBP, HBX2 = H3 || HBX, HNCX = H1 || HBX2;
+  float2 bx = fma_opt<H2, HBP, PK>(nrt, b, bp);
+  bx = fma_opt<H3, HBX, PK>(nk1, g3, bx);
+  float2 m  = H1 ? f2mul<PK>(g1, hx) : zero;
+  float2 ncx = HBX2 ? f2mul<PK>(xi, bx) : zero;
+  ncx = fma_opt<H1, HBX2, PK>(nrt, m, ncx);
+  // y
+  constexpr bool HBY = H1 || HBP, HBY2 = H4 || HBY, HNCY = H2 || HBY2;
+  float2 by = fma_opt<H1, HBP, PK>(nrt, a, bp);
+  by = fma_opt<H4, HBY, PK>(nk1, g4, by);
+  float2 m2 = H2 ? f2mul<PK>(g2, hy) : zero;
+  float2 ncy = HBY2 ? f2mul<PK>(et, by) : zero;
+  ncy = fma_opt<H2, HBY2, PK>(nrt, m2, ncy);
+  // h
+  float2 nhh = HNCX ? f2mul<PK>(xi, ncx) : zero;
+  nhh = fma_opt<HNCY, HNCX, PK>(et, ncy, nhh);
+  nhh = fma_opt<HQ, HNCX || HNCY, PK>(nk1, q, nhh);
+  nhh = fma_opt<HAB, HNCX || HNCY || HQ, PK>(k2p, ab, nhh);
+  if (HAB || HBP) acc[0] = f2fma<PA>(E, PE, acc[0]);
+  if (HNCX) acc[1] = f2fma<PA>(E, ncx, acc[1]);
+  if (HNCY) acc[2] = f2fma<PA>(E, ncy, acc[2]);
+  if (HNCX || HNCY || HQ || HAB) acc[3] = f2fma<PA>(E, nhh, acc[3]);
+}
+
 // final per-node factors: dW = A_W/e, dc = W rt/e * (-A_c), dd likewise, dh = W rt/(e sigma) * (-A_h)
 SP_HD void g2_bwd_finish(float h, float W, float aW, float nAc, float nAd, float nAh,
                          float* dW, float* dc, float* dd, float* dh) {
@@ -226,9 +284,12 @@ SP_HD void g2_bwd_finish(float h, float W, float aW, float nAc, float nAd, float
 // own per-pair code: only (u_xx, u_yy) present -- Laplacian-type residuals such as the Poisson
 // configs -- and only u present -- Dirichlet boundary penalties.  With the absent terms removed
 // every remaining term shares one node-constant factor, which moves out of the sum over points.
-enum { BWD_ALL = 0, BWD_LAPL = 1, BWD_U = 2 };
+// BWD_MASKED + mask: the general algebra specialised at compile time on the upstream rows present
+// (g2_bwd_pair_mask); record layout, accumulators and node finish are those of BWD_ALL.
+enum { BWD_ALL = 0, BWD_LAPL = 1, BWD_U = 2, BWD_MASKED = 32 };
+SP_HD constexpr bool bwd_general(int mode) { return mode == BWD_ALL || mode >= BWD_MASKED; }
 SP_HD constexpr int bwd_nrec(int mode) { return mode == BWD_U ? 2 : 4; }
-SP_HD constexpr int bwd_nacc(int mode) { return mode == BWD_ALL ? 4 : mode == BWD_LAPL ? 5 : 4; }
+SP_HD constexpr int bwd_nacc(int mode) { return mode == BWD_LAPL ? 5 : 4; }
 
 // only g3 (u_xx), g4 (u_yy).  With a = xi^2, s = xi^2 + eta^2, phi = 2^{-s} (= E/e) and the
 // per-POINT constants D = g3-g4, m = -s2 (g3+g4), k3 = -2 s2 g3, k4 = -2 s2 g4 (s2 = sigma^2;
@@ -293,7 +354,7 @@ SP_HD void g2_bwd_pair_u(float2 x2, float2 y2, float2 g0, float2 nc, float2 nd, 
 template <int MODE>
 SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* dc, float* dd, float* dh) {
   const double rt = 1.0 / (SIG_D * (double)h);
-  if (MODE == BWD_ALL) {
+  if (bwd_general(MODE)) {
     g2_bwd_finish(h, W, a[0], a[1], a[2], a[3], dW, dc, dd, dh);
   } else if (MODE == BWD_LAPL) {
     // accumulators are in units of phi = E/e; a[3] holds sum(phi q s), the general form needs

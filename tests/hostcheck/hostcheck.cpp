@@ -8,6 +8,29 @@
 
 using namespace spinn;
 
+template <int MASK>
+static void hc_masked_impl(int N, int M, const float* x, const float* y, const float* g, const float* c,
+                           const float* d, const float* h, const float* W, float* dc, float* dd, float* dh,
+                           float* dW) {
+  int N2 = (N + 1) / 2;
+  for (int j = 0; j < M; ++j) {
+    G2BwdNode n = g2_bwd_node(c[j], d[j], h[j]);
+    float2 acc[4];
+    for (int a = 0; a < 4; ++a) acc[a] = f2(0.f, 0.f);
+    for (int p = 0; p < N2; ++p) {
+      int i0 = 2 * p, i1 = 2 * p + 1;
+      bool v = i1 < N;
+      float2 gg[5];
+      for (int a = 0; a < 5; ++a) gg[a] = f2(g[(size_t)a * N + i0], v ? g[(size_t)a * N + i1] : 0.f);
+      g2_bwd_pair_mask<MASK>(f2(x[i0], v ? x[i1] : x[i0]), f2(y[i0], v ? y[i1] : y[i0]), gg[0], gg[1], gg[2],
+                             gg[3], gg[4], f2dup(n.nc), f2dup(n.nd), f2dup(n.rp), f2dup(n.nrt), f2dup(n.rho),
+                             f2dup(n.nk1), f2dup(n.k2p), acc);
+    }
+    g2_bwd_finish(h[j], W[j], acc[0].x + acc[0].y, acc[1].x + acc[1].y, acc[2].x + acc[2].y,
+                  acc[3].x + acc[3].y, &dW[j], &dc[j], &dd[j], &dh[j]);
+  }
+}
+
 extern "C" {
 
 // fast forward emulation: jets [6][N]
@@ -26,6 +49,19 @@ void hc_g2_fwd(int N, int M, const float* x, const float* y, const float* c, con
                         f2(n0.w0, n1.w0), f2(n0.w1, n1.w1), f2(n0.w2, n1.w2), acc);
     }
     for (int a = 0; a < 6; ++a) jets[(size_t)a * N + i] = acc[a].x + acc[a].y + (a == 0 ? bias : 0.f);
+  }
+}
+
+// mask-specialised general backward (g2_bwd_pair_mask<MASK>): g [5][N] with the ABSENT rows holding
+// NaN (they must never enter the arithmetic); outputs dc, dd, dh, dW [M]
+void hc_g2_bwd_masked(int mask, int N, int M, const float* x, const float* y, const float* g, const float* c,
+                      const float* d, const float* h, const float* W, float* dc, float* dd, float* dh,
+                      float* dW) {
+  switch (mask) {
+    case 0x06: hc_masked_impl<0x06>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x0C: hc_masked_impl<0x0C>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x0F: hc_masked_impl<0x0F>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    default: hc_masked_impl<0x1F>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
   }
 }
 

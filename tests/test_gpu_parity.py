@@ -322,7 +322,7 @@ def test_beyond_baseline_size_16m_points_16384_nodes():
     assert torch.equal(flat, step.run(all_reduce=False))
 
 
-@pytest.mark.parametrize("mask", [0x18, 0x08, 0x10, 0x01, 0x19, 0x06, 0x1F])
+@pytest.mark.parametrize("mask", [0x18, 0x08, 0x10, 0x01, 0x19, 0x06, 0x0C, 0x0F, 0x1F])
 @pytest.mark.parametrize("kind,K", [("gaussian", 1), ("gaussian", 3), ("softplus", 1)])
 def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
     """present_mask: absent rows of gjets count as zero and are never read (they hold NaN here);

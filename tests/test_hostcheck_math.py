@@ -161,3 +161,29 @@ def test_structured_upstream_backward(hc, name, mode):
     assert mixed_err(dd, G["d_yc"]) < TOL
     assert mixed_err(dh, G["d_h"]) < TOL
     assert mixed_err(dW, G["d_W"][0]) < TOL
+
+
+@pytest.mark.parametrize("name", ["g2d_k1", "g2d_wide"])
+@pytest.mark.parametrize("mask", [0x06, 0x0C, 0x0F, 0x1F])
+def test_mask_specialised_general_backward(hc, name, mask):
+    """g2_bwd_pair_mask<MASK>: the general algebra with the absent upstream rows removed at compile
+    time (advection 0x06, heat 0x0C, Burgers 0x0F) equals the full formula with zeros in those rows;
+    the absent rows hold NaN here and must not be touched."""
+    c = load_case(name)
+    xc, yc, h = _nodes2d(c)
+    x, y, W = f32(c["x"]), f32(c["y"]), f32(c["W"]).reshape(-1)[:xc.size]
+    N, M = x.size, xc.size
+    g = f32(np.random.RandomState(mask).randn(5, N))
+    g6 = np.zeros((6, N, 1))
+    for a in range(5):
+        if (mask >> a) & 1:
+            g6[a, :, 0] = g[a]
+        else:
+            g[a] = np.nan
+    dc, dd, dh, dW = (np.zeros(M, np.float32) for _ in range(4))
+    hc.hc_g2_bwd_masked(mask, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W),
+                        _ptr(dc), _ptr(dd), _ptr(dh), _ptr(dW))
+    G = cf.grads2d("gaussian", x, y, xc, yc, h, W.reshape(1, -1), g6)
+    for got, key in ((dc, "d_xc"), (dd, "d_yc"), (dh, "d_h")):
+        assert np.isfinite(got).all() and mixed_err(got, G[key]) < TOL, (mask, key)
+    assert mixed_err(dW, G["d_W"][0]) < TOL
