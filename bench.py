@@ -116,12 +116,79 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# the reference's CPU algorithm (oracle port) -- cpu_baseline and --impl reference
+# the reference ITSELF (baseline/_ref/code, unmodified) -- cpu_baseline, --impl reference and the
+# same-GPU eager leg.  Falls back to the oracle port only when baseline/_ref is absent.
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup):
-    """Times oracle/torch_port.poisson_interior_step (dense (N,M) tensors + 3x autograd.grad +
-    backward: the reference's own algorithm, spinn2d.py:169-179 + pde2d_base.py:46-62 +
-    common.py:242-248) on a chunk of the same workload, all host threads."""
+def _perturb_reference_(nn, seed=0):
+    """The seeded parameter state of SURVEY.md 8(d) (same draws as spinn_b200.synthetic.perturb_,
+    restated here so that the reference arm imports nothing of spinn_b200)."""
+    g = torch.Generator().manual_seed(seed)
+    l1, l2 = nn.layer1, nn.layer2
+    dev = l2.weight.device
+    with torch.no_grad():
+        l2.weight.copy_((0.3 * torch.randn(l2.weight.shape, generator=g)).to(dev))
+        l1.h.mul_((1.0 + 0.3 * torch.rand(l1.h.shape, generator=g)).to(dev))
+        l1.x.add_((0.01 * torch.randn(l1.x.shape, generator=g)).to(dev))
+        l1.y.add_((0.01 * torch.randn(l1.y.shape, generator=g)).to(dev))
+        l2.bias.copy_((0.1 * torch.randn(l2.bias.shape, generator=g)).to(dev))
+
+
+def host_threads():
+    """All host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to its children)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def reference_run(args, device, chunk, steps, warmup):
+    """One step = the reference's own interior path on `chunk` of the workload's points:
+    SPINN2D.forward (code/spinn2d.py:169-179) -> RegularPDE._get_residue / _compute_derivatives
+    (code/pde2d_base.py:46-62,132-137) -> Poisson2D.pde (code/poisson2d_sine.py:16-18) ->
+    interior_loss (pde2d_base.py:139-141) -> backward (common.py:246), executed from
+    baseline/_ref/code.  Rate is size-independent."""
+    from baseline import reference_loader as rl
+    ref = rl.load("common", "spinn2d", "pde2d_base", "poisson2d_sine")
+    ref.common.device(device)
+    pde = ref.poisson2d_sine.Poisson2D(args.nodes, args.samples, args.b_nodes, None)
+    act = ref.spinn2d.gaussian if args.kind == "gaussian" else ref.spinn2d.SoftPlus()
+    nn = ref.spinn2d.SPINN2D(pde, act).to(ref.common.device())
+    _perturb_reference_(nn)
+    xs, ys = pde.p_samples
+    n_all = xs.numel()
+    chunk = min(chunk, n_all)
+    stride = max(1, n_all // chunk)                        # spread the sample over the whole grid
+    pde.p_samples = tuple(t.detach()[::stride][:chunk].clone().requires_grad_(True) for t in (xs, ys))
+    n = pde.p_samples[0].numel()
+    M = nn.layer1.n
+    sync = torch.cuda.synchronize if torch.device(device).type == "cuda" else (lambda: None)
+
+    def one():
+        nn.zero_grad()
+        for t in pde.p_samples:
+            t.grad = None
+        loss = pde.interior_loss(nn)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        one()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = one()
+    sync()
+    dt = time.perf_counter() - t0
+    return {"value": n * M * steps / dt, "ms_per_step": 1e3 * dt / steps, "points": n, "nodes": M,
+            "cores": torch.get_num_threads(), "nproc": os.cpu_count(), "loss": float(loss.detach()), "kind": "reference",
+            "what": "baseline/_ref/code (unmodified reference): SPINN2D.forward + RegularPDE._compute_derivatives "
+                    "(3x autograd.grad) + Poisson2D.pde + interior_loss + backward, dense (N,M) fp32 eager"}
+
+
+def port_run(args, steps, warmup):
+    """Oracle port (oracle/torch_port.py) -- only when baseline/_ref did not travel."""
     from oracle import torch_port as tp
     from spinn_b200 import common, synthetic
     common.device("cpu")
@@ -131,13 +198,12 @@ def cpu_reference_run(args, steps, warmup):
     n = xs.numel()
     l1, l2 = nn.layer1, nn.layer2
     M = l1.n
-    kind = args.kind
 
     def one():
         for t in (xs, ys, l1.x, l1.y, l1.h, l2.weight, l2.bias):
             t.grad = None
         xc, yc = l1.centers()
-        return tp.poisson_interior_step(kind, xs, ys, xc, yc, l1.h, l2.weight, l2.bias, float(args.samples))
+        return tp.poisson_interior_step(args.kind, xs, ys, xc, yc, l1.h, l2.weight, l2.bias, float(args.samples))
 
     for _ in range(warmup):
         one()
@@ -146,7 +212,16 @@ def cpu_reference_run(args, steps, warmup):
         one()
     dt = time.perf_counter() - t0
     return {"value": n * M * steps / dt, "ms_per_step": 1e3 * dt / steps, "points": n, "nodes": M,
-            "cores": torch.get_num_threads(), "nproc": os.cpu_count()}
+            "cores": torch.get_num_threads(), "nproc": os.cpu_count(), "kind": "port",
+            "what": "oracle/torch_port.py (dense eager port; baseline/_ref absent)"}
+
+
+def cpu_reference_run(args, steps, warmup):
+    from baseline import reference_loader as rl
+    host_threads()
+    if rl.available():
+        return reference_run(args, "cpu", args.cpu_chunk, steps, warmup)
+    return port_run(args, steps, warmup)
 
 
 def run_reference_arm(args):
@@ -154,8 +229,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     r = cpu_reference_run(args, args.steps, args.warmup)
-    sample = (f"{r['points']} of {args.samples} points x {r['nodes']} nodes per step, dense eager fp32 "
-              f"fwd+3x autograd.grad+backward (oracle/torch_port.py)")
+    sample = (f"{r['points']} of {args.samples} points x {r['nodes']} nodes per step, {r['what']}; "
+              f"{r['cores']} torch threads of {r['nproc']} cpus")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -164,7 +239,7 @@ def run_reference_arm(args):
         "config": {"workload": workload_name(args.kind, args.samples, r["nodes"]), "points": args.samples,
                    "nodes": r["nodes"], "kind": args.kind,
                    "sample": f"each step = {r['points']} of the {args.samples} points (bounded CPU sample)"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -603,48 +678,41 @@ def run_ours(args):
         except Exception as exc:  # pragma: no cover
             compact = {"error": repr(exc)[:200]}
 
-    # the reference's dense eager algorithm on THIS GPU (oracle port on cuda), largest chunk that fits
+    # the reference ITSELF (baseline/_ref/code) on THIS GPU, eager, at the largest point count that
+    # fits in HBM (~100 B per pair -> ~400K points at 4096 nodes)
     gpu_eager = None
     if ws == 1 and not args.no_cpu_baseline:
-        try:
-            from oracle import torch_port as tp
-            chunk = 65536
-            xg = xs[:chunk].clone().requires_grad_(True)
-            yg = ys[:chunk].clone().requires_grad_(True)
-            leaves = [t.detach().clone().requires_grad_(True) for t in (l1.x, l1.y, l1.h, l2.weight, l2.bias)]
-
-            def eager():
-                for t in leaves + [xg, yg]:
-                    t.grad = None
-                xc = torch.cat((leaves[0], l1.xf))
-                yc = torch.cat((leaves[1], l1.yf))
-                U = tp.forward2d(args.kind, xg, yg, xc, yc, leaves[2], leaves[3], leaves[4]).squeeze()
-                ux, uy = tp._d(U, (xg, yg))
-                uxx, _ = tp._d(ux, (xg, yg))
-                _, uyy = tp._d(uy, (xg, yg))
-                f = 20 * np.pi ** 2 * torch.sin(2 * np.pi * xg) * torch.sin(4 * np.pi * yg)
-                ((0.1 * (uxx + uyy + f)) ** 2).sum().div(N).backward()
-
-            eager()
-            ms_eager = time_call(eager, reps=3)
-            gpu_eager = {"value": chunk * M / (ms_eager * 1e-3), "unit": UNIT, "ms_per_chunk": ms_eager,
-                         "points_per_chunk": chunk,
-                         "what": "oracle/torch_port.py dense (N,M) eager + 3x autograd.grad + backward on the "
-                                 "same B200 (the reference's --gpu algorithm; it cannot hold more than "
-                                 "~400K points x 4096 nodes at ~100 B/pair)"}
-            del xg, yg, leaves
-            torch.cuda.empty_cache()
-        except Exception as exc:  # pragma: no cover
-            gpu_eager = {"error": repr(exc)[:200]}
+        from baseline import reference_loader as rl
+        del step
+        torch.cuda.empty_cache()
+        if rl.available():
+            tried = []
+            for chunk in (393216, 262144, 131072, 65536):
+                try:
+                    r = reference_run(args, dev, chunk, steps=3, warmup=1)
+                    gpu_eager = {"value": r["value"], "unit": UNIT, "ms_per_chunk": r["ms_per_step"],
+                                 "points_per_chunk": r["points"], "did_not_fit": tried, "kind": "reference",
+                                 "what": r["what"] + " -- on the same B200 (--gpu path), 3 reps after 1 warm-up"}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    tried.append(chunk)
+                except Exception as exc:  # pragma: no cover
+                    gpu_eager = {"error": repr(exc)[:200]}
+                    break
+                finally:
+                    import gc
+                    gc.collect()
+                    torch.cuda.empty_cache()
+        else:
+            gpu_eager = {"unavailable": "baseline/_ref/code did not travel"}
 
     cpu_baseline = None
     if ws == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, steps=3, warmup=1)
-        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                         "ms_per_sample_step": r["ms_per_step"],
                         "sample": f"{r['points']} of {N} points x {r['nodes']} nodes, 3 reps after 1 warm-up, "
-                                  f"dense eager fp32 fwd+3x autograd.grad+backward (oracle/torch_port.py), "
-                                  f"{r['cores']} torch threads of {r['nproc']} cpus"}
+                                  f"{r['what']}, {r['cores']} torch threads of {r['nproc']} cpus"}
         common.device(dev)
 
     line = {

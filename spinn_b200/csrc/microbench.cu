@@ -36,9 +36,10 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
     } else if (WHICH == 4) {     // FFMA2 with scalar-broadcast operand (as the kernels use): a = b*m.x + a
 #pragma unroll
       for (int k = 0; k < 8; ++k) a[k] = f2fma(b[k], f2dup(m.x), a[k]);
-    } else if (WHICH == 5) {     // FMUL2 + FADD2 alternating
+    } else if (WHICH == 5) {     // 8 FMUL2 + 8 FADD2 on INDEPENDENT chains (a *= m; b += d), so that
+                                 // ptxas cannot contract a pair into one FFMA2 (SASS checked: tools/microbench.py)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = f2mul(a[k], m); a[k] = f2add(a[k], d); }
+      for (int k = 0; k < 8; ++k) { a[k] = f2mul(a[k], m); b[k] = f2add(b[k], d); }
     } else if (WHICH == 6) {     // scalar FFMA with immediate addend: a = a*m + 1e-9
 #pragma unroll
       for (int k = 0; k < 8; ++k) { a[k].x = fmaf(a[k].x, m.x, 1e-9f); a[k].y = fmaf(a[k].y, m.y, 1e-9f); }
@@ -67,6 +68,30 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
         for (int k = 0; k < 8; ++k) a[k] = f2fma(b[k], f2dup(m.x), a[k]);
       if (WHICH >= 13) { c[0].x = ex2f_fast(-c[0].x); c[0].y = ex2f_fast(-c[0].y); }
       if (WHICH == 14) { c[1].x = ex2f_fast(-c[1].x); c[1].y = ex2f_fast(-c[1].y); }
+    } else if (WHICH == 15) {    // FMUL2 only, shared operand: a = a*m
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = f2mul(a[k], m);
+    } else if (WHICH == 16) {    // FADD2 only, shared operand: a = a+d
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = f2add(a[k], d);
+    } else if (WHICH == 17) {    // FMUL2 only, two distinct pairs: a = a*b
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = f2mul(a[k], b[k]);
+    } else if (WHICH == 18) {    // FADD2 only, two distinct pairs: a = a+b
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = f2add(a[k], b[k]);
+    } else if (WHICH == 19) {    // the forward kernel's own instruction mix per node pair and point, on
+                                 // independent register chains: 7 FFMA2 : 4 FMUL2 : 3 FADD2 : 2 MUFU.EX2
+      a[0] = f2add(a[0], d); a[1] = f2add(a[1], d);                 // X, Y
+      a[2] = f2mul(a[2], m); a[3] = f2mul(a[3], m);                 // xi, eta
+      a[4] = f2fma(a[4], m, d); a[5] = f2fma(a[5], m, d);           // hx, hy
+      a[6] = f2add(a[6], d);                                        // t
+      c[0].x = ex2f_fast(-c[0].x); c[0].y = ex2f_fast(-c[0].y);     // E
+      b[0] = f2fma(b[1], m, b[0]);                                  // u
+      a[7] = f2mul(a[7], m);                                        // g
+      b[2] = f2fma(b[3], c[2], b[2]); b[4] = f2fma(b[3], c[3], b[4]);   // ux, uy
+      c[4] = f2mul(c[4], m);                                        // e
+      b[5] = f2fma(b[6], c[5], b[5]); b[7] = f2fma(b[6], c[6], b[7]);   // uxx, uyy
     } else if (WHICH == 12) {    // FFMA2 where b, c reused across two consecutive instrs (reuse cache)
 #pragma unroll
       for (int k = 0; k < 8; k += 2) { a[k] = f2fma(b[k], c[k], a[k]); a[k + 1] = f2fma(b[k], c[k], a[k + 1]); }
@@ -76,6 +101,10 @@ probe_kernel(int iters, const float* __restrict__ in, float* sink) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y + b[k].x;
   if (WHICH >= 11) s += c[0].x + c[0].y + c[1].x + c[1].y;     // keep the MUFU results live
+  if (WHICH == 5 || WHICH == 19) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += b[k].y + c[k].x + c[k].y;
+  }
   if (s == 123.456f) sink[0] = s;
 }
 
@@ -100,6 +129,11 @@ extern "C" int spinn_microbench(int which, int iters, int blocks, int threads, c
     case 12: probe_kernel<12><<<blocks, threads, 0, s>>>(iters, in, sink); break;
     case 13: probe_kernel<13><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 32.0; break;
     case 14: probe_kernel<14><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 32.0; break;
+    case 15: probe_kernel<15><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 16: probe_kernel<16><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 17: probe_kernel<17><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 18: probe_kernel<18><<<blocks, threads, 0, s>>>(iters, in, sink); break;
+    case 19: probe_kernel<19><<<blocks, threads, 0, s>>>(iters, in, sink); per_iter = 28.0; break;  /* 14 packed instr */
     default: return -1;
   }
   if (lane_ops) *lane_ops = lanes * per_iter;

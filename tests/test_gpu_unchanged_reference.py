@@ -1,0 +1,52 @@
+"""The reference's OWN problem scripts (baseline/_ref/code/*.py -- a byte-for-byte copy of
+/root/reference/code made by __graft_entry__.build()) executed unchanged as `__main__` with `--gpu`
+on a B200, driving the CUDA kernels through spinn_b200/dropin; loss histories are compared with the
+ones recorded from the stock reference (tests/golden/traj_*.npz, tests/golden/make_golden.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CODE = os.path.join(ROOT, "baseline", "_ref", "code")
+
+
+def test_reference_copy_is_present_where_the_reference_exists():
+    """Build container: build() must have produced baseline/_ref/code (it ships with the snapshot)."""
+    if not os.path.isdir("/root/reference/code"):
+        pytest.skip("no /root/reference here")
+    sys.path.insert(0, ROOT)
+    from baseline import reference_loader as rl
+    assert rl.install() and rl.available()
+    import filecmp
+    for name in ("spinn2d.py", "pde2d_base.py", "poisson2d_sine.py", "cavity.py", "ode3.py", "common.py"):
+        assert filecmp.cmp(os.path.join("/root/reference/code", name), os.path.join(REF_CODE, name), shallow=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,traj", [
+    ("poisson2d_sine", "poisson2d_sine"), ("cavity", "cavity"), ("ode3", "ode3"),
+    ("poisson2d_irreg_dom", "irreg"), ("heat1d", "heat1d"), ("burgers1d", "burgers1d")])
+def test_unchanged_reference_script_runs_on_the_cuda_kernels(script, traj, tmp_path):
+    if not os.path.isfile(os.path.join(REF_CODE, script + ".py")):
+        pytest.skip("baseline/_ref/code did not travel with this snapshot (run __graft_entry__.build() "
+                    "in the build container first)")
+    d = np.load(os.path.join(GOLDEN, f"traj_{traj}.npz"))
+    ref, args, ref_err = d["loss"], [str(a) for a in d["args"]], d["errors"]
+    out = str(tmp_path / "out.npz")
+    runner = os.path.join(ROOT, "tests", "run_unchanged_reference_on_gpu.py")
+    subprocess.check_call([sys.executable, "-W", "ignore", runner, ROOT, out, script] + args)
+    got = np.load(out)
+    loss = got["loss"]
+    assert len(loss) == len(ref), (len(loss), len(ref))
+    # every closure = interior + boundary forward through the C ABI, one fused backward each
+    assert int(got["forward_calls"]) >= 2 * len(ref) and int(got["backward_calls"]) >= len(ref)
+    rel = np.abs(loss - ref) / np.abs(ref)
+    assert rel[:10].max() < 5e-5, (script, rel[:10].max())
+    assert rel.max() < 3e-3, (script, rel.max())
+    if ref_err[2] > 0:
+        assert abs(got["errors"][2] - ref_err[2]) < 0.01 * ref_err[2] + 1e-6, (script, got["errors"], ref_err)

@@ -11,13 +11,34 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spinn_b200 import _cabi  # noqa: E402
 
 NAMES = ["FFMA a=a*m+d (shared regs)", "FFMA a=b*c+a (3 distinct regs)", "FFMA2 a=a*m+d (shared)",
-         "FFMA2 a=b*c+a (3 distinct pairs)", "FFMA2 a=b*bcast+a", "FMUL2+FADD2", "FFMA a=a*m+imm",
+         "FFMA2 a=b*c+a (3 distinct pairs)", "FFMA2 a=b*bcast+a", "8 FMUL2 + 8 FADD2 (independent chains)",
+         "FFMA a=a*m+imm",
          "half FFMA2 + half FFMA (distinct)", "FADD distinct", "FMUL distinct", "MUFU.EX2",
          "16 FFMA2 bcast (no MUFU)", "FFMA2 operands reused pairwise", "16 FFMA2 bcast + 2 MUFU.EX2",
-         "16 FFMA2 bcast + 4 MUFU.EX2"]
+         "16 FFMA2 bcast + 4 MUFU.EX2", "FMUL2 a=a*m (shared)", "FADD2 a=a+d (shared)",
+         "FMUL2 a=a*b (2 distinct pairs)", "FADD2 a=a+b (2 distinct pairs)",
+         "fwd mix 7 FFMA2:4 FMUL2:3 FADD2:2 EX2"]
+
+
+def sass_census():
+    """Static check that each probe's loop holds the instructions its name claims (cuobjdump)."""
+    import collections
+    import re
+    import subprocess
+    for which in range(len(NAMES)):
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", f"_Z12probe_kernelILi{which}EEviPKfPf", _cabi.LIB_PATH],
+                             capture_output=True, text=True).stdout
+        ops = collections.Counter()
+        for line in out.splitlines():
+            m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+            if m and m.group(1) in ("FFMA", "FFMA2", "FMUL", "FMUL2", "FADD", "FADD2", "MUFU"):
+                ops[m.group(1)] += 1
+        print(f"# SASS census probe {which:2d} ({NAMES[which]}): " + ", ".join(f"{k} {v}" for k, v in sorted(ops.items())))
 
 
 def main():
+    if "--sass" in sys.argv:
+        sass_census()
     lib = _cabi.load()
     dev = torch.device("cuda", 0)
     src = (1.0 + 1e-3 * torch.rand(64, device=dev)).float()
