@@ -145,6 +145,11 @@ int spinn2d_jets_bwd_sparse(int kind, int level, int present_mask, int N, int M_
                             unsigned long long* stats, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* ---- development hook (tools/tune.py): select kernel tile-shape variants, "fwd=<id>,bwd=<id>,waves=<n>";
+ * NULL restores the defaults.  The same string is read ONCE from the environment variable SPINN_TUNE
+ * when the library is loaded; the compute entry points never read the environment. */
+void spinn_set_tuning(const char* spec);
+
 /* ---- instruction-throughput probes used to measure the roofline denominators on the box
  * (spinn_b200/csrc/microbench.cu).  Every thread runs 8 independent float2 accumulator chains
  * for `iters` iterations with operands held in registers loaded from `in` (>= 64 floats), so
@@ -153,7 +158,9 @@ int spinn2d_jets_bwd_sparse(int kind, int level, int present_mask, int N, int M_
  *   0 FFMA a=a*m+d (shared regs)   1 FFMA a=b*c+a (3 distinct regs)   2 FFMA2 a=a*m+d
  *   3 FFMA2 a=b*c+a (3 distinct register pairs)   4 FFMA2 with a scalar-broadcast operand
  *   5 FMUL2+FADD2   6 FFMA with immediate   7 half FFMA2 / half FFMA   8 FADD   9 FMUL
- *   10 MUFU.EX2   11 (reserved)   12 FFMA2 with pairwise-reused operands */
+ *   10 MUFU.EX2   11/13/14 16 FFMA2 (broadcast operand) + 0/2/4 MUFU.EX2   12 FFMA2 with pairwise-reused
+ *   operands   15 FMUL2 a=a*m   16 FADD2 a=a+d   17 FMUL2 a=a*b   18 FADD2 a=a+b
+ *   19 the Gaussian forward's instruction mix (7 FFMA2 : 4 FMUL2 : 3 FADD2 : 2 MUFU.EX2) */
 int spinn_microbench(int which, int iters, int blocks, int threads, const float* in, float* sink,
                      double* lane_ops, void* stream);
 

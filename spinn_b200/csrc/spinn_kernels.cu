@@ -18,6 +18,7 @@
 //   * GENERIC every other (dim, kernel, K<=4, level): scalar arithmetic built on
 //            phi_derivs_* (same tiling, same reduction).
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -139,29 +140,38 @@ __global__ void pack_nodes_soa_kernel(int M, int Mfree, int Mp, int K,
 }
 
 // fast forward records: one per NODE PAIR (j, j+1), three float4:
-//   {nc_j, nc_j1, nd_j, nd_j1} {rp_j, rp_j1, w0_j, w0_j1} {w1_j, w1_j1, w2_j, w2_j1}
-__global__ void pack_nodes_g2fwd_kernel(int M, int Mfree, int npairs,
+//   Gaussian     {nc_j, nc_j1, nd_j, nd_j1} {rp_j, rp_j1, w0_j, w0_j1} {w1_j, w1_j1, w2_j, w2_j1}
+//   softplus-hat {nc.., nd..} {c1.., w0..} {w1.., w2..}                       (S2FwdNode)
+template <int KIND>
+__global__ void pack_nodes_k1fwd_kernel(int M, int Mfree, int npairs,
                                         const float* __restrict__ xf, const float* __restrict__ yf,
                                         const float* __restrict__ xfix, const float* __restrict__ yfix,
                                         const float* __restrict__ h, int hs,
                                         const float* __restrict__ W, float4* __restrict__ recs) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
-  G2FwdNode n[2];
+  float v[2][6];
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
     int j = 2 * p + l;
+    float c = 0.f, d = 0.f, hh = 1.f, w = 0.f;             // padding node: contributes exactly zero
     if (j < M) {
-      float c = j < Mfree ? xf[j] : xfix[j - Mfree];
-      float d = j < Mfree ? yf[j] : yfix[j - Mfree];
-      n[l] = g2_fwd_node(c, d, hs ? h[0] : h[j], W[j]);
+      c = j < Mfree ? xf[j] : xfix[j - Mfree];
+      d = j < Mfree ? yf[j] : yfix[j - Mfree];
+      hh = hs ? h[0] : h[j];
+      w = W[j];
+    }
+    if (KIND == GAUSSIAN) {
+      const G2FwdNode n = g2_fwd_node(c, d, hh, w);
+      v[l][0] = n.nc; v[l][1] = n.nd; v[l][2] = n.rp; v[l][3] = n.w0; v[l][4] = n.w1; v[l][5] = n.w2;
     } else {
-      n[l] = g2_fwd_node(0.f, 0.f, 1.f, 0.f);
+      const S2FwdNode n = s2_fwd_node(c, d, hh, w);
+      v[l][0] = n.nc; v[l][1] = n.nd; v[l][2] = n.c1; v[l][3] = n.w0; v[l][4] = n.w1; v[l][5] = n.w2;
     }
   }
-  recs[3 * (size_t)p + 0] = make_float4(n[0].nc, n[1].nc, n[0].nd, n[1].nd);
-  recs[3 * (size_t)p + 1] = make_float4(n[0].rp, n[1].rp, n[0].w0, n[1].w0);
-  recs[3 * (size_t)p + 2] = make_float4(n[0].w1, n[1].w1, n[0].w2, n[1].w2);
+  recs[3 * (size_t)p + 0] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+  recs[3 * (size_t)p + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+  recs[3 * (size_t)p + 2] = make_float4(v[0][4], v[1][4], v[0][5], v[1][5]);
 }
 
 // fast backward records: one per POINT PAIR (i, i+1), bwd_nrec(MODE) float4 each:
@@ -227,24 +237,61 @@ static const BwdCfg BWD_CFGS[] = {
     {2, 256, 4, 256},  // 6  (as 2 with 64 registers/thread, 4 CTAs/SM)
     {4, 128, 3, 256},  // 7
 };
+// softplus-hat fast backward: node tile = q*threads (lanes are node pairs, q even)
+static const BwdCfg S2_BWD_CFGS[] = {
+    {2, 256, 2, 256},  // 0  512-node tile (default)
+    {2, 128, 4, 256},  // 1  256-node tile
+    {2, 64, 8, 256},   // 2  128-node tile
+    {2, 32, 16, 256},  // 3  64-node tile
+};
+constexpr int N_S2_BWD_CFGS = sizeof(S2_BWD_CFGS) / sizeof(S2_BWD_CFGS[0]);
 constexpr int N_FWD_CFGS = sizeof(FWD_CFGS) / sizeof(FWD_CFGS[0]);
 constexpr int N_BWD_CFGS = sizeof(BWD_CFGS) / sizeof(BWD_CFGS[0]);
 constexpr int FWD_DEFAULT = 3, BWD_DEFAULT = 2, WAVES_DEFAULT = 2;   // picked with tools/tune.py on B200
 
+// The knobs live in three atomics: parsed from SPINN_TUNE ONCE when the library is loaded, changed
+// afterwards only through spinn_set_tuning() (tools/tune.py).  The entry points never touch the
+// environment.
 struct Tune { int fwd, bwd, waves; bool bwd_forced; };
-static Tune get_tune() {
-  Tune t = {FWD_DEFAULT, BWD_DEFAULT, WAVES_DEFAULT, false};
-  const char* e = getenv("SPINN_TUNE");
+static std::atomic<int> g_tune_fwd{FWD_DEFAULT}, g_tune_bwd{-1}, g_tune_waves{WAVES_DEFAULT};
+
+static void parse_tuning(const char* e) {
+  int fwd = FWD_DEFAULT, bwd = -1, waves = WAVES_DEFAULT;
   if (e) {
     const char* q;
-    if ((q = strstr(e, "fwd="))) t.fwd = atoi(q + 4);
-    if ((q = strstr(e, "bwd="))) { t.bwd = atoi(q + 4); t.bwd_forced = true; }
-    if ((q = strstr(e, "waves="))) t.waves = atoi(q + 6);
+    if ((q = strstr(e, "fwd="))) fwd = atoi(q + 4);
+    if ((q = strstr(e, "bwd="))) bwd = atoi(q + 4);
+    if ((q = strstr(e, "waves="))) waves = atoi(q + 6);
   }
-  if (t.fwd < 0 || t.fwd >= N_FWD_CFGS) t.fwd = FWD_DEFAULT;
-  if (t.bwd < 0 || t.bwd >= N_BWD_CFGS) t.bwd = BWD_DEFAULT;
-  if (t.waves < 1 || t.waves > 64) t.waves = WAVES_DEFAULT;
+  if (fwd < 0 || fwd >= N_FWD_CFGS) fwd = FWD_DEFAULT;
+  if (bwd >= N_BWD_CFGS) bwd = -1;
+  if (waves < 1 || waves > 64) waves = WAVES_DEFAULT;
+  g_tune_fwd.store(fwd); g_tune_bwd.store(bwd); g_tune_waves.store(waves);
+}
+namespace { struct TuneInit { TuneInit() { parse_tuning(getenv("SPINN_TUNE")); } } g_tune_init; }
+
+static Tune get_tune() {
+  Tune t;
+  t.fwd = g_tune_fwd.load(std::memory_order_relaxed);
+  const int b = g_tune_bwd.load(std::memory_order_relaxed);
+  t.bwd_forced = b >= 0;
+  t.bwd = b >= 0 ? b : BWD_DEFAULT;
+  t.waves = g_tune_waves.load(std::memory_order_relaxed);
   return t;
+}
+
+// cudaFuncSetAttribute once per (kernel instantiation, device); safe with concurrent host threads
+struct OnceFlags {
+  std::atomic<int> st[64];
+  OnceFlags() { for (auto& v : st) v.store(0); }
+};
+template <class F>
+static cudaError_t opt_in_smem_once(OnceFlags& flags, int dev, F kfn, int bytes) {
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (flags.st[dev].load(std::memory_order_acquire) == 1) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) flags.st[dev].store(1, std::memory_order_release);   // idempotent: a race repeats the call
+  return e;
 }
 
 // -----------------------------------------------------------------------------
@@ -297,37 +344,92 @@ __device__ __forceinline__ void store_points(float* __restrict__ p, long long i0
     if (i0 + q < N) p[i0 + q] = v[q];
 }
 
-template <int P, bool MIXED, int UNROLL>
-__device__ __forceinline__ void g2k1_fwd_inner(const float4* __restrict__ sm4, int n,
-                                               const float2* x2, const float2* y2,
-                                               float2 (*acc)[MIXED ? 6 : 5]) {
+template <int KIND, int P, bool MIXED, int UNROLL>
+__device__ __forceinline__ void k1_fwd_inner(const float4* __restrict__ sm4, int n,
+                                             const float2* x2, const float2* y2,
+                                             float2 (*acc)[MIXED ? 6 : 5]) {
 #pragma unroll UNROLL
   for (int p = 0; p < n; ++p) {
     const float4 A = sm4[3 * p + 0], B = sm4[3 * p + 1], C = sm4[3 * p + 2];
     const float2 nc = f2(A.x, A.y), nd = f2(A.z, A.w), rp = f2(B.x, B.y);
     const float2 w0 = f2(B.z, B.w), w1 = f2(C.x, C.y), w2 = f2(C.z, C.w);
 #pragma unroll
-    for (int q = 0; q < P; ++q) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+    for (int q = 0; q < P; ++q) {
+      if (KIND == GAUSSIAN) g2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+      else s2_fwd_pair<MIXED>(x2[q], y2[q], nc, nd, rp, w0, w1, w2, acc[q]);
+    }
   }
 }
 
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
-__global__ void __launch_bounds__(THREADS, MINB)
-g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
-                const float4* __restrict__ recs, int npairs, int tile_pairs,
-                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+// One span of the point set, walked in warp-tiles of 32*P consecutive points: tile `wt` of the span
+// starts at point `base + wt*32*P`; the span ends at `end`.  COOP: all warps of the CTA run the same
+// number of iterations (the multi-tile node loop has block-wide barriers).
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP>
+__device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N, const float* __restrict__ x,
+                                            const float* __restrict__ y, const float4* __restrict__ recs,
+                                            const float4* __restrict__ sm4w, float4* __restrict__ sm4, int npairs,
+                                            int tile_pairs, float b0, float* __restrict__ jets, bool vec,
+                                            long long gw, long long nwarps) {
   constexpr int NJ = MIXED ? 6 : 5;
-  constexpr int WPC = THREADS / 32;
-  extern __shared__ float4 sm4[];
   const int lane = threadIdx.x & 31;
-  // slot-major warp rank: warps 0-3 of every CTA first, then warps 4-7, ... so that the LAST
-  // (partial) wave of warp-tiles is spread over all SMs / sub-partitions instead of leaving
-  // whole CTAs idle
+  const long long nwt = (end - base + 32 * P - 1) / (32 * P);
+  const long long iters = (nwt + nwarps - 1) / nwarps;
+  for (long long it = 0; it < iters; ++it) {
+    const long long wt = gw + it * nwarps;
+    const bool active = wt < nwt;                  // warp-uniform
+    if (!COOP && !active) break;
+    const long long i0 = base + (wt * 32 + lane) * P;
+    const int lim = (int)end;                      // points at or beyond `end` belong to another span
+    float px[P], py[P];
+    load_points<P>(x, active ? i0 : (long long)lim, lim, vec, px);
+    load_points<P>(y, active ? i0 : (long long)lim, lim, vec, py);
+    float2 x2[P], y2[P], acc[P][NJ];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      x2[q] = f2dup(px[q]);
+      y2[q] = f2dup(py[q]);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
+    }
+    if (!COOP) {
+      k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4w, npairs, x2, y2, acc);
+    } else {
+      for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
+        const int n = min(tile_pairs, npairs - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 3 * n; e += THREADS) sm4[e] = recs[3 * (size_t)t0 + e];
+        __syncthreads();
+        k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4, n, x2, y2, acc);
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) {
+        float out[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
+        // `lim` (not N) bounds the stores of this span; the jets rows are N long
+        store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
+      }
+    }
+  }
+}
+
+// Persistent CTAs.  Main span: as many FULL rounds (every warp one tile of 32*P points) as fit;
+// the remainder -- less than one round -- is walked with one point per thread (tiles of 32 points), so
+// that the last, partial round keeps (nearly) every warp of every SM busy at half the work instead of
+// leaving half of the warps idle (8-GPU shards: 3.46 rounds -> 3 rounds + one half-size round).
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL>
+__device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, const float* __restrict__ y,
+                                            const float4* __restrict__ recs, int npairs, int tile_pairs,
+                                            const float* __restrict__ bias, float* __restrict__ jets,
+                                            int vec_ok, float4* sm4) {
+  constexpr int WPC = THREADS / 32;
+  // slot-major warp rank: warps 0-3 of every CTA first, then warps 4-7, ... so that a partial
+  // round of warp-tiles is spread over all SMs / sub-partitions instead of leaving whole CTAs idle
   const int lw = threadIdx.x >> 5;
   const long long gw = (long long)(lw >> 2) * ((long long)gridDim.x * 4) + (long long)blockIdx.x * 4 + (lw & 3);
   const long long nwarps = (long long)gridDim.x * WPC;
-  const long long nwt = ((long long)N + 32 * P - 1) / (32 * P);
-  const long long iters = (nwt + nwarps - 1) / nwarps;
   const bool single = npairs <= tile_pairs;
   const bool vec = vec_ok != 0;
   const float b0 = bias ? bias[0] : 0.f;
@@ -348,44 +450,36 @@ g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                      min(TMA_CHUNK, bytes - off), &bar);
     }
     mbar_wait(&bar, 0);
+    const long long round_pts = nwarps * 32 * P;
+    const long long main_end = P == 1 ? (long long)N : ((long long)N / round_pts) * round_pts;
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false>(0, main_end, N, x, y, recs, sm4, sm4, npairs, tile_pairs,
+                                                        b0, jets, vec, gw, nwarps);
+    if (P > 1 && main_end < N)
+      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
+                                                          tile_pairs, b0, jets, vec, gw, nwarps);
+  } else {
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
+                                                       jets, vec, gw, nwarps);
   }
-  for (long long it = 0; it < iters; ++it) {
-    const long long wt = gw + it * nwarps;
-    const bool active = wt < nwt;                  // warp-uniform
-    if (single && !active) break;                  // no further block-level syncs on this path
-    const long long i0 = (wt * 32 + lane) * P;
-    float px[P], py[P];
-    load_points<P>(x, active ? i0 : (long long)N, N, vec, px);
-    load_points<P>(y, active ? i0 : (long long)N, N, vec, py);
-    float2 x2[P], y2[P], acc[P][NJ];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-      x2[q] = f2dup(px[q]);
-      y2[q] = f2dup(py[q]);
-#pragma unroll
-      for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
-    }
-    if (single) {
-      g2k1_fwd_inner<P, MIXED, UNROLL>(sm4, npairs, x2, y2, acc);
-    } else {
-      for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
-        const int n = min(tile_pairs, npairs - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < 3 * n; e += THREADS) sm4[e] = recs[3 * (size_t)t0 + e];
-        __syncthreads();
-        g2k1_fwd_inner<P, MIXED, UNROLL>(sm4, n, x2, y2, acc);
-      }
-    }
-    if (active) {
-#pragma unroll
-      for (int a = 0; a < NJ; ++a) {
-        float out[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
-        store_points<P>(jets + (size_t)a * N, i0, N, vec, out);
-      }
-    }
-  }
+}
+
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB)
+g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
+                const float4* __restrict__ recs, int npairs, int tile_pairs,
+                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+  extern __shared__ float4 sm4[];
+  k1_fwd_body<GAUSSIAN, P, MIXED, THREADS, UNROLL>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4);
+}
+
+// the same persistent, TMA-staged forward with the softplus-hat pair function (spinn_math.cuh, FAST PATH 2)
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB)
+s2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
+                const float4* __restrict__ recs, int npairs, int tile_pairs,
+                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+  extern __shared__ float4 sm4[];
+  k1_fwd_body<SOFTPLUS, P, MIXED, THREADS, UNROLL>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4);
 }
 
 // -----------------------------------------------------------------------------
@@ -561,6 +655,111 @@ g2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
       out[2 * (size_t)Mp + j] = dh;
       out[3 * (size_t)Mp + j] = dW;
     }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// FAST backward, softplus-hat: 2-D, K=1, level <= 2.  Same skeleton as g2k1_bwd_kernel (thread =
+// Q nodes in registers, point-pair record tiles through a TMA bulk-copy ring, partial sums per
+// (chunk, node), no atomics); the two lanes of every packed instruction are two adjacent NODES, the
+// point's coordinates and upstream gradients are scalar-broadcast operands.  Records use the
+// general layout {x,x',y,y'} {g0,g0',g1,g1'} {g2,g2',g3,g3'} {g4,g4',0,0}.  MASK: upstream rows
+// present (compile-time pruned, s2_bwd_pair<MASK>).
+// -----------------------------------------------------------------------------
+template <int Q, int THREADS, int MINB, int TILE, int MASK>
+__global__ void __launch_bounds__(THREADS, MINB)
+s2k1_bwd_kernel(int N2, int pairs_per_chunk, const float4* __restrict__ ptrecs,
+                const float* __restrict__ soa, int Mp, float* __restrict__ partials) {
+  static_assert(Q % 2 == 0, "lanes are node pairs");
+  constexpr int NREC = 4, NACC = 5, QS = Q / 2, NS = 2;
+  __shared__ __align__(16) float4 ring[NS][NREC * TILE];
+  __shared__ __align__(8) uint64_t full[NS];
+  const int jblock = blockIdx.x * (Q * THREADS);
+  float2 nc[QS], nd[QS], c1[QS], cr[QS], ncr[QS], nrho2[QS];
+  float hq[Q], wq[Q];
+#pragma unroll
+  for (int q = 0; q < QS; ++q) {
+    const int j = jblock + 2 * (q * THREADS + threadIdx.x);
+    const float2 c = *reinterpret_cast<const float2*>(soa + j);
+    const float2 d = *reinterpret_cast<const float2*>(soa + (size_t)Mp + j);
+    const float2 h = *reinterpret_cast<const float2*>(soa + 2 * (size_t)Mp + j);
+    const float2 w = *reinterpret_cast<const float2*>(soa + 4 * (size_t)Mp + j);
+    hq[2 * q] = h.x; hq[2 * q + 1] = h.y;
+    wq[2 * q] = w.x; wq[2 * q + 1] = w.y;
+    const S2BwdNode n0 = s2_bwd_node(c.x, d.x, h.x), n1 = s2_bwd_node(c.y, d.y, h.y);
+    nc[q] = f2(n0.nc, n1.nc); nd[q] = f2(n0.nd, n1.nd); c1[q] = f2(n0.c1, n1.c1);
+    cr[q] = f2(n0.cr, n1.cr); ncr[q] = f2(n0.ncr, n1.ncr); nrho2[q] = f2(n0.nrho2, n1.nrho2);
+  }
+  float2 tot[QS][NACC];
+#pragma unroll
+  for (int q = 0; q < QS; ++q)
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) tot[q][a] = f2(0.f, 0.f);
+
+  const int p_begin = blockIdx.y * pairs_per_chunk;
+  const int p_end = min(N2, p_begin + pairs_per_chunk);
+  const int ntiles = p_end > p_begin ? (p_end - p_begin + TILE - 1) / TILE : 0;
+  auto issue = [&](int t) {                    // thread 0 only
+    const int t0 = p_begin + t * TILE;
+    const unsigned bytes = (unsigned)(min(TILE, p_end - t0) * NREC) * (unsigned)sizeof(float4);
+    mbar_expect_tx(&full[t % NS], bytes);
+    tma_bulk_g2s(ring[t % NS], ptrecs + NREC * (size_t)t0, bytes, &full[t % NS]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NS - 1 && i < ntiles; ++i) issue(i);
+  for (int t = 0; t < ntiles; ++t) {
+    const int t0 = p_begin + t * TILE;
+    const int n = min(TILE, p_end - t0);
+    const float4* sm4 = ring[t % NS];
+    if (threadIdx.x == 0 && t + NS - 1 < ntiles) issue(t + NS - 1);
+    mbar_wait(&full[t % NS], (unsigned)((t / NS) & 1));
+    float2 acc[QS][NACC];
+#pragma unroll
+    for (int q = 0; q < QS; ++q)
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[q][a] = f2(0.f, 0.f);
+#pragma unroll 1
+    for (int p = 0; p < n; ++p) {
+      const float4 A = sm4[NREC * p + 0];
+      float4 B = make_float4(0.f, 0.f, 0.f, 0.f), C = B, D = B;
+      if (MASK & 0x03) B = sm4[NREC * p + 1];
+      if (MASK & 0x0C) C = sm4[NREC * p + 2];
+      if (MASK & 0x10) D = sm4[NREC * p + 3];
+#pragma unroll
+      for (int q = 0; q < QS; ++q) {
+        s2_bwd_pair<MASK>(f2dup(A.x), f2dup(A.z), f2dup(B.x), f2dup(B.z), f2dup(C.x), f2dup(C.z), f2dup(D.x),
+                          nc[q], nd[q], c1[q], cr[q], ncr[q], nrho2[q], acc[q]);
+        s2_bwd_pair<MASK>(f2dup(A.y), f2dup(A.w), f2dup(B.y), f2dup(B.w), f2dup(C.y), f2dup(C.w), f2dup(D.y),
+                          nc[q], nd[q], c1[q], cr[q], ncr[q], nrho2[q], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < QS; ++q)
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) { tot[q][a].x += acc[q][a].x; tot[q][a].y += acc[q][a].y; }
+    __syncthreads();                                   // everyone is done reading this stage
+  }
+  // rows: 0 dc, 1 dd, 2 dh, 3 dW
+  float* out = partials + (size_t)blockIdx.y * 4 * Mp;
+#pragma unroll
+  for (int q = 0; q < QS; ++q) {
+    const int j = jblock + 2 * (q * THREADS + threadIdx.x);
+    float t0[NACC], t1[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) { t0[a] = tot[q][a].x; t1[a] = tot[q][a].y; }
+    float2 dW, dc, dd, dh;
+    s2_bwd_finish(hq[2 * q], wq[2 * q], t0, &dW.x, &dc.x, &dd.x, &dh.x);
+    s2_bwd_finish(hq[2 * q + 1], wq[2 * q + 1], t1, &dW.y, &dc.y, &dd.y, &dh.y);
+    *reinterpret_cast<float2*>(out + j) = dc;
+    *reinterpret_cast<float2*>(out + (size_t)Mp + j) = dd;
+    *reinterpret_cast<float2*>(out + 2 * (size_t)Mp + j) = dh;
+    *reinterpret_cast<float2*>(out + 3 * (size_t)Mp + j) = dW;
   }
 }
 
@@ -822,6 +1021,37 @@ add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ o
 }
 
 // -----------------------------------------------------------------------------
+// fast forward launcher (one instantiation per kernel kind / tile shape)
+// -----------------------------------------------------------------------------
+struct FastFwdArgs {
+  int N; const float* x; const float* y; const float4* recs; int npairs, tile_pairs;
+  const float* bias; float* jets; int vec_ok; size_t smem; int sms, dev; cudaStream_t s;
+};
+
+template <int KIND, int P, int T, int B, int U, bool MIXED>
+static int launch_fast_fwd_m(const FastFwdArgs& a) {
+  const long long nwt = ((long long)a.N + 32 * P - 1) / (32 * P);
+  long long blocks = (nwt + (T / 32) - 1) / (T / 32);
+  if (blocks > (long long)a.sms * B) blocks = (long long)a.sms * B;
+  static OnceFlags once;
+  if (KIND == GAUSSIAN) {
+    auto kfn = g2k1_fwd_kernel<P, MIXED, T, B, U>;
+    CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
+    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok);
+  } else {
+    auto kfn = s2k1_fwd_kernel<P, MIXED, T, B, U>;
+    CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
+    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok);
+  }
+  LAUNCH_CHECK(KIND == GAUSSIAN ? "g2k1_fwd_kernel" : "s2k1_fwd_kernel");
+  return SPINN_OK;
+}
+template <int KIND, int P, int T, int B, int U>
+static int launch_fast_fwd(bool mixed, const FastFwdArgs& a) {
+  return mixed ? launch_fast_fwd_m<KIND, P, T, B, U, true>(a) : launch_fast_fwd_m<KIND, P, T, B, U, false>(a);
+}
+
+// -----------------------------------------------------------------------------
 // planning
 // -----------------------------------------------------------------------------
 struct FwdPlan {
@@ -832,7 +1062,7 @@ struct FwdPlan {
 };
 
 static bool fwd_is_fast(int dim, int kind, int level, int K) {
-  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && (level == 2 || level == 3);
+  return dim == 2 && K == 1 && (level == 2 || level == 3);
 }
 
 static FwdPlan plan_fwd(int dim, int kind, int level, int M, int K) {
@@ -864,7 +1094,8 @@ struct BwdPlan {
 };
 
 static bool bwd_is_fast(int dim, int kind, int level, int K) {
-  return dim == 2 && kind == SPINN_KIND_GAUSSIAN && K == 1 && level <= 2;
+  (void)kind;
+  return dim == 2 && K == 1 && level <= 2;
 }
 
 // effective upstream mask: bit a set <=> row a of gjets is present; 0 on input means "all"
@@ -888,6 +1119,7 @@ static int chunks_for(int sms, int waves, int groups, long long units, int tile,
   long long target = (long long)sms * blocks_per_sm * waves;
   int c = (int)((target + groups - 1) / groups);
   if (c < 1) c = 1;
+  if (c > 65535) c = 65535;                    // grid.y limit
   // chunk length: whole smem tiles for large point sets; for small ones a finer granularity
   // (the tile loop handles partial tiles) so that a few hundred points still spread over many CTAs
   long long per = (units + c - 1) / c;
@@ -916,7 +1148,17 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
   // 256-node tile 1.015, 128-node tile 1.06, 64-node tile ~1.10), unless SPINN_TUNE pins one
   // The structured modes also have a 1024-node tile (two node-pair streams per thread, 3 % faster
   // than the 512-node tile at M = 4096).
-  if (!tune.bwd_forced) {
+  const bool sp = kind == SPINN_KIND_SOFTPLUS;
+  if (sp) {
+    const double cost[N_S2_BWD_CFGS] = {1.0, 1.015, 1.06, 1.10};
+    double best = 1e300;
+    p.variant = 0;
+    for (int i = 0; i < N_S2_BWD_CFGS; ++i) {
+      const BwdCfg c = S2_BWD_CFGS[i];
+      const double w = (double)round_up_i(M, c.q * c.threads) * cost[i];
+      if (w < best) { best = w; p.variant = i; }
+    }
+  } else if (!tune.bwd_forced) {
     const int cand[5] = {2, 0, 1, 4, 5};
     const double cost[5] = {1.0, 1.015, 1.06, 1.10, 0.97};
     double best = 1e300;
@@ -926,7 +1168,7 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
       if (w < best) { best = w; p.variant = cand[i]; }
     }
   }
-  const BwdCfg cfg = BWD_CFGS[p.variant];
+  const BwdCfg cfg = sp ? S2_BWD_CFGS[p.variant] : BWD_CFGS[p.variant];
   const int group = cfg.q * cfg.threads;
   const int Mp_fast = round_up_i(M, group);
   int pc_fast = 0;
@@ -938,8 +1180,8 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
   if (worst) {
     part_floats = (size_t)c_gen * nacc * Mp_gen;
     Mp_w = Mp_gen;
-    for (int v = 0; v < N_BWD_CFGS; ++v) {
-      const BwdCfg c = BWD_CFGS[v];
+    for (int v = 0; v < N_BWD_CFGS + N_S2_BWD_CFGS; ++v) {
+      const BwdCfg c = v < N_BWD_CFGS ? BWD_CFGS[v] : S2_BWD_CFGS[v - N_BWD_CFGS];
       const int g = c.q * c.threads, mp = round_up_i(M, g);
       int pc = 0;
       const int waves = tune.waves > 8 ? tune.waves : 8;
@@ -1052,9 +1294,13 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
 
   if (p.fast) {
     float4* recs = (float4*)ws;
-    pack_nodes_g2fwd_kernel<<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
-                                                                      xfix, yfix, h, hs, W, recs);
-    LAUNCH_CHECK("pack_nodes_g2fwd_kernel");
+    if (kind == SPINN_KIND_GAUSSIAN)
+      pack_nodes_k1fwd_kernel<GAUSSIAN><<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
+                                                                                  xfix, yfix, h, hs, W, recs);
+    else
+      pack_nodes_k1fwd_kernel<SOFTPLUS><<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
+                                                                                  xfix, yfix, h, hs, W, recs);
+    LAUNCH_CHECK("pack_nodes_k1fwd_kernel");
     const int tile_pairs = p.npairs < 2048 ? p.npairs : 2048;
     const size_t smem = (size_t)3 * tile_pairs * sizeof(float4);
     const int vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)jets) % 16 == 0) && (N % 4 == 0);
@@ -1062,40 +1308,20 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const Tune tune = get_tune();
     const int sms = sm_count();
     int cur_dev = 0;
-    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
-#define SPINN_LAUNCH_FAST_FWD(P_, T_, B_, U_)                                                               \
-  do {                                                                                              \
-    const long long nwt = ((long long)N + 32 * P_ - 1) / (32 * P_);                                 \
-    long long blocks = (nwt + (T_ / 32) - 1) / (T_ / 32);                                           \
-    if (blocks > (long long)sms * B_) blocks = (long long)sms * B_;                                 \
-    if (mixed) {                                                                                    \
-      auto kfn = g2k1_fwd_kernel<P_, true, T_, B_, U_>;                                             \
-      static bool configured[64] = {false}; /* once per instantiation and device (not in capture) */ \
-      if (!configured[cur_dev]) {                                                                   \
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
-        configured[cur_dev] = true;                                                                 \
-      }                                                                                             \
-      kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
-    } else {                                                                                        \
-      auto kfn = g2k1_fwd_kernel<P_, false, T_, B_, U_>;                                            \
-      static bool configured[64] = {false};                                                         \
-      if (!configured[cur_dev]) {                                                                   \
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));   \
-        configured[cur_dev] = true;                                                                 \
-      }                                                                                             \
-      kfn<<<(int)blocks, T_, smem, s>>>(N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok);   \
-    }                                                                                               \
-  } while (0)
+    if (cudaGetDevice(&cur_dev) != cudaSuccess) cur_dev = -1;
     // small point sets: one point per thread so that every SM gets work
     const bool small = (long long)N < (long long)32 * 4 * 8 * sms;
     const int v = small ? 2 : tune.fwd;
+    const bool sp = kind == SPINN_KIND_SOFTPLUS;
+    const FastFwdArgs fa = {N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok, smem, sms, cur_dev, s};
+    int rcl;
     switch (v) {
-      case 0: SPINN_LAUNCH_FAST_FWD(4, 256, 2, 2); break;
-      case 1: SPINN_LAUNCH_FAST_FWD(2, 512, 2, 2); break;
-      case 2: SPINN_LAUNCH_FAST_FWD(1, 512, 2, 4); break;
-      default: SPINN_LAUNCH_FAST_FWD(2, 256, 2, 4); break;
+      case 0: rcl = sp ? launch_fast_fwd<SOFTPLUS, 4, 256, 2, 1>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 4, 256, 2, 2>(mixed, fa); break;
+      case 1: rcl = sp ? launch_fast_fwd<SOFTPLUS, 2, 512, 2, 1>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 2, 512, 2, 2>(mixed, fa); break;
+      case 2: rcl = sp ? launch_fast_fwd<SOFTPLUS, 1, 512, 2, 2>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 1, 512, 2, 4>(mixed, fa); break;
+      default: rcl = sp ? launch_fast_fwd<SOFTPLUS, 2, 256, 2, 2>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 2, 256, 2, 4>(mixed, fa); break;
     }
-#undef SPINN_LAUNCH_FAST_FWD
+    if (rcl) return rcl;
     LAUNCH_CHECK("g2k1_fwd_kernel");
     return SPINN_OK;
   }
@@ -1160,7 +1386,30 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
   LAUNCH_CHECK("pack_nodes_soa_kernel");
 
   dim3 grid(p.node_groups, p.chunks);
-  if (p.fast) {
+  if (p.fast && kind == SPINN_KIND_SOFTPLUS) {
+    float4* ptrecs = (float4*)(base + p.off_pts);
+    const int pgrid = ceil_div_i(p.N2, 256);
+    pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    LAUNCH_CHECK("pack_points_g2bwd_kernel");
+    const int sm = (mask == 0x01) ? 0x01 : ((mask & ~0x18) == 0 ? 0x18 : 0x1F);
+#define SPINN_LAUNCH_S2_BWD(Q_, T_, B_, TILE_)                                                                 \
+  do {                                                                                                        \
+    if (sm == 0x01)                                                                                           \
+      s2k1_bwd_kernel<Q_, T_, B_, TILE_, 0x01><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else if (sm == 0x18)                                                                                      \
+      s2k1_bwd_kernel<Q_, T_, B_, TILE_, 0x18><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+    else                                                                                                      \
+      s2k1_bwd_kernel<Q_, T_, B_, TILE_, 0x1F><<<grid, T_, 0, s>>>(p.N2, p.per_chunk, ptrecs, soa, p.Mp, partials); \
+  } while (0)
+    switch (p.variant) {
+      case 1: SPINN_LAUNCH_S2_BWD(2, 128, 4, 256); break;
+      case 2: SPINN_LAUNCH_S2_BWD(2, 64, 8, 256); break;
+      case 3: SPINN_LAUNCH_S2_BWD(2, 32, 16, 256); break;
+      default: SPINN_LAUNCH_S2_BWD(2, 256, 2, 256); break;
+    }
+#undef SPINN_LAUNCH_S2_BWD
+    LAUNCH_CHECK("s2k1_bwd_kernel");
+  } else if (p.fast) {
     float4* ptrecs = (float4*)(base + p.off_pts);
     const int mode = bwd_mode_for(mask);
     const int pgrid = ceil_div_i(p.N2, 256);
@@ -1228,6 +1477,7 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
 extern "C" {
 
 int spinn_abi_version(void) { return SPINN_ABI_VERSION; }
+void spinn_set_tuning(const char* spec) { parse_tuning(spec); }
 const char* spinn_last_error(void) { return g_err; }
 
 int spinn_num_jets(int dim, int level) {

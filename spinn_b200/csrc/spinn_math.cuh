@@ -374,6 +374,183 @@ SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* d
   }
 }
 
+// =============================================================================
+// FAST PATH 2: 2-D softplus-hat, one output (K=1), packed lanes = two NODES.
+//
+// phi = S(z)/F,  z = k - sp(2s) - sp(-2s) - sp(2t) - sp(-2t),  s = (x-c)/h, t = (y-d)/h
+// (reference code/spinn2d.py:195-205).  With e_x = exp(-2s), A_x = 1 + e_x (any sign of s: the
+// expressions below are invariant under e -> 1/e, so no |s| and no copysign are needed; the exponent
+// is clamped at 2^40 so that nothing overflows):
+//   w = e^z = EK e_x e_y / (A_x A_y)^2,   sigma = w/(1+w),   i = 1/(1+w) = 1 - sigma,
+//   S = ln(1+w),   tanh s = (1-e_x)/A_x,
+//   F phi_x   = -sigma tau,                        tau = 2 r tanh s,  ups = 2 r tanh t,  r = 1/h
+//   F phi_xx  = sigma [tau^2 (i + 1/2) - 2 rho],   rho = r^2
+//   F phi_xy  = sigma i tau ups
+//   F phi_xxx = sigma tau [2 rho (3i+1) - tau^2 (2 i^2 + i/2 + 1/2)]
+//   F phi_xyy = sigma i tau [2 rho - (2i - 1/2) ups^2]
+// (sigma' = sigma i, sigma'' = sigma i (2i-1), sech^2 = 1 - tanh^2 substituted; verified against
+// oracle/closed_form.py in fp64 to 1e-15, tests/test_hostcheck_math.py.)
+// 5 MUFU per pair (2 EX2, 2 RCP, 1 LG2) + 30 packed FP32 instructions forward.  A_x, A_y carry the
+// factor q^-1 = EK^-1/4 so that R = 1/(A_x' A_y') squares to EK/(A_x A_y)^2 without an extra multiply.
+// The series branches of the generic path (log1p / 1-e for small arguments) are not needed at the
+// level of the SUMS over nodes / points: their absolute errors (~1e-7 of the largest term) are
+// those of fp32 rounding; `LOGFIX` adds the first-order correction of the rounding of 1+w.
+// =============================================================================
+constexpr float HAT_Q_F    = 2.568050838266732f;       // EK2^(1/4)
+constexpr float HAT_IQ_F   = 0.3894003907940293f;      // 1/q
+constexpr float HAT_IQ2_F  = 0.15163266435054276f;     // 1/q^2
+constexpr float HAT_HIQ2_F = 0.07581633217527138f;     // 1/(2 q^2)
+constexpr double HAT_Q_D   = 2.568050838266732;
+constexpr float HAT_PCLAMP = 40.0f;                    // log2 of the largest e = exp(-2s) kept
+
+SP_HD float2 f2min_s(float2 a, float m) { return make_float2(fminf(a.x, m), fminf(a.y, m)); }
+SP_HD float2 f2ex2(float2 t) { return make_float2(ex2f_fast(t.x), ex2f_fast(t.y)); }
+SP_HD float2 f2rcp(float2 t) { return make_float2(rcpf_fast(t.x), rcpf_fast(t.y)); }
+SP_HD float2 f2lg2(float2 t) { return make_float2(lg2f_fast(t.x), lg2f_fast(t.y)); }
+
+// forward node record: nc=-c, nd=-d, c1=-2 log2(e)/h, w0=W ln2/F, w1=-2 r W/(F q), w2=4 rho W/F
+struct S2FwdNode { float nc, nd, c1, w0, w1, w2; };
+SP_HD S2FwdNode s2_fwd_node(float c, float d, float h, float W) {
+  const double r = 1.0 / (double)h, Wf = (double)W / HAT_FAC_D;
+  S2FwdNode n;
+  n.nc = -c; n.nd = -d;
+  n.c1 = (float)(-2.0 * 1.4426950408889634074 * r);
+  n.w0 = (float)(Wf * 0.69314718055994530942);
+  n.w1 = (float)(-2.0 * r * Wf / HAT_Q_D);
+  n.w2 = (float)(4.0 * r * r * Wf);
+  return n;
+}
+
+// shared head of forward and backward: X, Y, e_x, e_y, A_x', A_y', R, 1+w, i, sigma
+struct S2Head { float2 X, Y, ex, ey, Ax, Ay, R, opw, i, sg; };
+SP_HD S2Head s2_head(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1) {
+  const float2 iq = f2dup(HAT_IQ_F), one = f2dup(1.0f);
+  S2Head h;
+  h.X = f2add(x2, nc); h.Y = f2add(y2, nd);
+  const float2 px = f2min_s(f2mul(h.X, c1), HAT_PCLAMP), py = f2min_s(f2mul(h.Y, c1), HAT_PCLAMP);
+  h.ex = f2ex2(px); h.ey = f2ex2(py);
+  h.Ax = f2fma(h.ex, iq, iq); h.Ay = f2fma(h.ey, iq, iq);
+  h.R = f2rcp(f2mul(h.Ax, h.Ay));
+  const float2 ee = f2mul(h.ex, h.ey), R2 = f2mul(h.R, h.R);
+  const float2 w = f2mul(ee, R2);
+  h.opw = f2add(w, one);
+  h.i = f2rcp(h.opw);
+  h.sg = f2mul(w, h.i);
+  return h;
+}
+
+// acc: u, ux, uy, uxx, uyy (, uxy); lanes = partial sums over one node parity
+template <bool MIXED>
+SP_HD void s2_fwd_pair(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1, float2 w0, float2 w1,
+                       float2 w2, float2* acc) {
+  const float2 one = f2dup(1.0f), neg1 = f2dup(-1.0f);
+  const S2Head h = s2_head(x2, y2, nc, nd, c1);
+  acc[0] = f2fma(w0, f2lg2(h.opw), acc[0]);
+  const float2 omx = f2fma(h.ex, neg1, one), omy = f2fma(h.ey, neg1, one);
+  const float2 Tx = f2mul(omx, f2mul(h.Ay, h.R)), Ty = f2mul(omy, f2mul(h.Ax, h.R));   // q tanh
+  const float2 e1 = f2mul(w1, h.sg);
+  acc[1] = f2fma(e1, Tx, acc[1]);
+  acc[2] = f2fma(e1, Ty, acc[2]);
+  const float2 b = f2fma(h.i, f2dup(HAT_IQ2_F), f2dup(HAT_HIQ2_F));                    // (i + 1/2)/q^2
+  const float2 hx = f2fma(f2mul(Tx, Tx), b, f2dup(-0.5f)), hy = f2fma(f2mul(Ty, Ty), b, f2dup(-0.5f));
+  const float2 e2 = f2mul(w2, h.sg);
+  acc[3] = f2fma(e2, hx, acc[3]);
+  acc[4] = f2fma(e2, hy, acc[4]);
+  if (MIXED) {
+    const float2 m = f2mul(f2mul(e2, h.i), f2dup(HAT_IQ2_F));
+    acc[5] = f2fma(m, f2mul(Tx, Ty), acc[5]);
+  }
+}
+
+// backward node constants: nc, nd, c1 as above; cr = 2r/q, ncr = -cr, nrho2 = -2 rho
+struct S2BwdNode { float nc, nd, c1, cr, ncr, nrho2; };
+SP_HD S2BwdNode s2_bwd_node(float c, float d, float h) {
+  const double r = 1.0 / (double)h;
+  S2BwdNode n;
+  n.nc = -c; n.nd = -d;
+  n.c1 = (float)(-2.0 * 1.4426950408889634074 * r);
+  n.cr = (float)(2.0 * r / HAT_Q_D);
+  n.ncr = -n.cr;
+  n.nrho2 = (float)(-2.0 * r * r);
+  return n;
+}
+
+// m = (have ? m + g P : g P)
+SP_HD void s2_term(bool& have, float2& m, float2 g, float2 P) {
+  m = have ? f2fma(g, P, m) : f2mul(g, P);
+  have = true;
+}
+
+// Backward pair, written in t = -tau, v = -ups so that every term enters with a plus sign
+// (F phi_x = sigma t, ...):
+//   mdc = g0 t + g1 Pxx + g2 Pxy + g3 Pxxx + g4 Pxyy      (= -F dc_ij / (W sigma))
+//   mdd = g0 v + g1 Pxy + g2 Pyy + g3 Pxxy + g4 Pyyy
+//   B1 = g1 t + g2 v,  A2 = g3 Pxx + g4 Pyy,  dWin = A2 + B1,  ord = 2 A2 + B1
+// acc[0] += sigma dWin; acc[1] += sigma mdc; acc[2] += sigma mdd; acc[3] += sigma (X mdc + Y mdd + ord);
+// acc[4] += g0 log2(1+w) (only when MASK & 1).  Rows absent from MASK are never read.
+template <int MASK>
+SP_HD void s2_bwd_pair(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, float2 g3, float2 g4,
+                       float2 nc, float2 nd, float2 c1, float2 cr, float2 ncr, float2 nrho2, float2* acc) {
+  constexpr bool H0 = MASK & 1, H1 = MASK & 2, H2 = MASK & 4, H3 = MASK & 8, H4 = MASK & 16;
+  const float2 zero = f2(0.f, 0.f), half = f2dup(0.5f);
+  const S2Head h = s2_head(x2, y2, nc, nd, c1);
+  const float2 t = f2mul(f2fma(h.ex, cr, ncr), f2mul(h.Ay, h.R));
+  const float2 v = f2mul(f2fma(h.ey, cr, ncr), f2mul(h.Ax, h.R));
+  float2 mdc = zero, mdd = zero, B1 = zero, A2 = zero;
+  bool hc = false, hd = false, hb = false, ha = false;
+  if (H0) {
+    acc[4] = f2fma(g0, f2lg2(h.opw), acc[4]);
+    s2_term(hc, mdc, g0, t);
+    s2_term(hd, mdd, g0, v);
+  }
+  if (H1 || H2 || H3 || H4) {
+    const float2 ta = f2mul(t, t), tb = f2mul(v, v);
+    const float2 ih = f2add(h.i, half);
+    const float2 Pxx = f2fma(ta, ih, nrho2), Pyy = f2fma(tb, ih, nrho2);
+    if (H1 || H2) {
+      const float2 Pxy = f2mul(h.i, f2mul(t, v));
+      if (H1) { s2_term(hb, B1, g1, t); s2_term(hc, mdc, g1, Pxx); s2_term(hd, mdd, g1, Pxy); }
+      if (H2) { s2_term(hb, B1, g2, v); s2_term(hc, mdc, g2, Pxy); s2_term(hd, mdd, g2, Pyy); }
+    }
+    if (H3 || H4) {
+      const float2 nc3 = f2mul(nrho2, f2fma(h.i, f2dup(3.0f), f2dup(1.0f)));          // -2 rho (3i+1)
+      const float2 pol = f2fma(h.i, f2fma(h.i, f2dup(2.0f), half), half);             // 2i^2 + i/2 + 1/2
+      const float2 c4n = f2fma(h.i, f2dup(2.0f), f2dup(-0.5f));                       // 2i - 1/2
+      if (H3) {
+        s2_term(ha, A2, g3, Pxx);
+        s2_term(hc, mdc, g3, f2mul(t, f2fma(ta, pol, nc3)));                         // Pxxx
+        s2_term(hd, mdd, g3, f2mul(f2mul(h.i, v), f2fma(ta, c4n, nrho2)));           // Pxxy
+      }
+      if (H4) {
+        s2_term(ha, A2, g4, Pyy);
+        s2_term(hc, mdc, g4, f2mul(f2mul(h.i, t), f2fma(tb, c4n, nrho2)));           // Pxyy
+        s2_term(hd, mdd, g4, f2mul(v, f2fma(tb, pol, nc3)));                         // Pyyy
+      }
+    }
+  }
+  if (ha || hb) {
+    const float2 dWin = (ha && hb) ? f2add(A2, B1) : (ha ? A2 : B1);
+    acc[0] = f2fma(h.sg, dWin, acc[0]);
+  }
+  if (hc) {
+    const float2 ord = (ha && hb) ? f2fma(A2, f2dup(2.0f), B1) : (ha ? f2add(A2, A2) : B1);
+    acc[1] = f2fma(h.sg, mdc, acc[1]);
+    acc[2] = f2fma(h.sg, mdd, acc[2]);
+    float2 hin = (ha || hb) ? f2fma(h.X, mdc, ord) : f2mul(h.X, mdc);
+    hin = f2fma(h.Y, mdd, hin);
+    acc[3] = f2fma(h.sg, hin, acc[3]);
+  }
+}
+
+// per-node finish: dW = (ln2 a4 + a0)/F, dc = -(W/F) a1, dd = -(W/F) a2, dh = -(W r/F) a3
+SP_HD void s2_bwd_finish(float h, float W, const float* a, float* dW, float* dc, float* dd, float* dh) {
+  const double iF = 1.0 / HAT_FAC_D, r = 1.0 / (double)h;
+  *dW = (float)((0.69314718055994530942 * (double)a[4] + (double)a[0]) * iF);
+  *dc = (float)(-(double)W * iF * (double)a[1]);
+  *dd = (float)(-(double)W * iF * (double)a[2]);
+  *dh = (float)(-(double)W * r * iF * (double)a[3]);
+}
+
 // number of jets / upstream-gradient slots per "level"
 //   2-D: level 0: u | 1: u,ux,uy | 2: u,ux,uy,uxx,uyy | 3: + uxy
 //   1-D: level 0: u | 1: u,ux    | 2: u,ux,uxx

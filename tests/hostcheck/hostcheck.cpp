@@ -256,3 +256,66 @@ void hc_generic_bwd2(int dim, int kind, int level, int K, int N, int M, const fl
 }
 
 }  // extern "C"
+
+// ---- softplus-hat fast path (s2_fwd_pair / s2_bwd_pair<MASK>): same loop structure as the kernels ----
+template <int MASK>
+static void hc_s2_bwd_impl(int N, int M, const float* x, const float* y, const float* g, const float* c,
+                           const float* d, const float* h, const float* W, float* dc, float* dd, float* dh,
+                           float* dW) {
+  // lanes = two adjacent NODES (as in the kernel); points one at a time, broadcast
+  for (int j = 0; j < M; j += 2) {
+    const bool v1 = j + 1 < M;
+    const S2BwdNode n0 = s2_bwd_node(c[j], d[j], h[j]);
+    const S2BwdNode n1 = v1 ? s2_bwd_node(c[j + 1], d[j + 1], h[j + 1]) : s2_bwd_node(0.f, 0.f, 1.f);
+    float2 acc[5];
+    for (int a = 0; a < 5; ++a) acc[a] = f2(0.f, 0.f);
+    for (int i = 0; i < N; ++i) {
+      float2 gg[5];
+      for (int a = 0; a < 5; ++a) gg[a] = f2dup(g[(size_t)a * N + i]);
+      s2_bwd_pair<MASK>(f2dup(x[i]), f2dup(y[i]), gg[0], gg[1], gg[2], gg[3], gg[4], f2(n0.nc, n1.nc),
+                        f2(n0.nd, n1.nd), f2(n0.c1, n1.c1), f2(n0.cr, n1.cr), f2(n0.ncr, n1.ncr),
+                        f2(n0.nrho2, n1.nrho2), acc);
+    }
+    float a0[5], a1[5];
+    for (int a = 0; a < 5; ++a) { a0[a] = acc[a].x; a1[a] = acc[a].y; }
+    s2_bwd_finish(h[j], W[j], a0, &dW[j], &dc[j], &dd[j], &dh[j]);
+    if (v1) s2_bwd_finish(h[j + 1], W[j + 1], a1, &dW[j + 1], &dc[j + 1], &dd[j + 1], &dh[j + 1]);
+  }
+}
+
+extern "C" {
+
+// jets [6][N]
+void hc_s2_fwd(int N, int M, const float* x, const float* y, const float* c, const float* d,
+               const float* h, const float* W, float bias, float* jets) {
+  int npairs = (M + 1) / 2;
+  std::vector<S2FwdNode> nodes(2 * npairs);
+  for (int j = 0; j < 2 * npairs; ++j)
+    nodes[j] = j < M ? s2_fwd_node(c[j], d[j], h[j], W[j]) : s2_fwd_node(0.f, 0.f, 1.f, 0.f);
+  for (int i = 0; i < N; ++i) {
+    float2 acc[6];
+    for (int a = 0; a < 6; ++a) acc[a] = f2(0.f, 0.f);
+    for (int p = 0; p < npairs; ++p) {
+      const S2FwdNode &n0 = nodes[2 * p], &n1 = nodes[2 * p + 1];
+      s2_fwd_pair<true>(f2dup(x[i]), f2dup(y[i]), f2(n0.nc, n1.nc), f2(n0.nd, n1.nd), f2(n0.c1, n1.c1),
+                        f2(n0.w0, n1.w0), f2(n0.w1, n1.w1), f2(n0.w2, n1.w2), acc);
+    }
+    for (int a = 0; a < 6; ++a) jets[(size_t)a * N + i] = acc[a].x + acc[a].y + (a == 0 ? bias : 0.f);
+  }
+}
+
+// g [5][N] with NaN in the rows absent from `mask`; outputs dc, dd, dh, dW [M]
+void hc_s2_bwd(int mask, int N, int M, const float* x, const float* y, const float* g, const float* c,
+               const float* d, const float* h, const float* W, float* dc, float* dd, float* dh, float* dW) {
+  switch (mask) {
+    case 0x01: hc_s2_bwd_impl<0x01>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x18: hc_s2_bwd_impl<0x18>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x07: hc_s2_bwd_impl<0x07>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x06: hc_s2_bwd_impl<0x06>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x0C: hc_s2_bwd_impl<0x0C>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    case 0x10: hc_s2_bwd_impl<0x10>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+    default: hc_s2_bwd_impl<0x1F>(N, M, x, y, g, c, d, h, W, dc, dd, dh, dW); break;
+  }
+}
+
+}  // extern "C"

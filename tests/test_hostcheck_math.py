@@ -187,3 +187,67 @@ def test_mask_specialised_general_backward(hc, name, mask):
     for got, key in ((dc, "d_xc"), (dd, "d_yc"), (dh, "d_h")):
         assert np.isfinite(got).all() and mixed_err(got, G[key]) < TOL, (mask, key)
     assert mixed_err(dW, G["d_W"][0]) < TOL
+
+
+# ---- softplus-hat fast path (2-D, K=1): s2_fwd_pair / s2_bwd_pair<MASK> ---------------------
+@pytest.mark.parametrize("name", [n for n in OP_CASES_2D if n.startswith("s2d") and load_case(n)["K"] == 1])
+def test_fast_softplus_forward(hc, name):
+    c = load_case(name)
+    xc, yc, h = _nodes2d(c)
+    x, y, W, b = f32(c["x"]), f32(c["y"]), f32(c["W"]).reshape(-1), f32(c["b"])
+    N, M = x.size, xc.size
+    jets = np.zeros((6, N), np.float32)
+    hc.hc_s2_fwd(N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), ctypes.c_float(b[0]), _ptr(jets))
+    ref = cf.jets2d("softplus", x, y, xc, yc, h, W.reshape(1, -1), b)[:, :, 0]
+    for a in range(6):
+        # bar: 2e-5, or twice what the REFERENCE's own fp32 path is off from its fp64 evaluation on this
+        # fixture (cancellation-dominated elements: s2d_k1 u_x, reference fp32 1.33e-5)
+        bar = TOL if a == 5 else max(TOL, 2.0 * mixed_err(c["jets_f32"][a, :, 0], c["jets_f64"][a, :, 0]))
+        assert mixed_err(jets[a], ref[a]) < bar, (name, a, mixed_err(jets[a], ref[a]))
+
+
+@pytest.mark.parametrize("mask", [0x1F, 0x18, 0x01, 0x07, 0x06, 0x0C, 0x10])
+@pytest.mark.parametrize("name", [n for n in OP_CASES_2D if n.startswith("s2d") and load_case(n)["K"] == 1])
+def test_fast_softplus_backward_all_masks(hc, name, mask):
+    c = load_case(name)
+    xc, yc, h = _nodes2d(c)
+    x, y, W = f32(c["x"]), f32(c["y"]), f32(c["W"]).reshape(-1)
+    N, M = x.size, xc.size
+    g = f32(c["gjets"][:5, :, 0]).copy()
+    g6 = np.zeros((6, N, 1))
+    for a in range(5):
+        if (mask >> a) & 1:
+            g6[a, :, 0] = g[a]
+        else:
+            g[a] = np.nan                                   # absent rows must never be read
+    dc, dd, dh, dW = (np.zeros(M, np.float32) for _ in range(4))
+    hc.hc_s2_bwd(mask, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W),
+                 _ptr(dc), _ptr(dd), _ptr(dh), _ptr(dW))
+    G = cf.grads2d("softplus", x, y, xc, yc, h, W.reshape(1, -1), g6)
+    for got, key in ((dc, "d_xc"), (dd, "d_yc"), (dh, "d_h"), (dW, "d_W")):
+        ref = np.asarray(G[key]).reshape(-1)
+        assert mixed_err(got, ref) < TOL, (name, hex(mask), key, mixed_err(got, ref))
+
+
+def test_fast_softplus_far_field_and_extreme_offsets(hc):
+    """Points up to 60 widths from a node on either side (clamped exponent, e -> inf / 0): finite and
+    equal to the oracle; a point exactly on a node centre."""
+    xc, yc, h, W = f32([0.5, -3.0]), f32([0.5, 4.0]), f32([0.05, 0.1]), f32([0.7, -0.4])
+    x = f32([0.5, 0.5 + 3.0, 0.5 - 3.0, 0.52, -3.0, 2.0, -6.0])
+    y = f32([0.5, 0.5 - 3.0, 0.5 + 3.0, 0.47, 4.0, -2.0, 9.0])
+    N, M = x.size, xc.size
+    jets = np.zeros((6, N), np.float32)
+    hc.hc_s2_fwd(N, M, _ptr(x), _ptr(y), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W), ctypes.c_float(0.0), _ptr(jets))
+    assert np.isfinite(jets).all()
+    ref = cf.jets2d("softplus", x, y, xc, yc, h, W.reshape(1, -1), np.zeros(1))[:, :, 0]
+    for a in range(6):
+        assert mixed_err(jets[a], ref[a]) < TOL, a
+    g = f32(np.random.RandomState(2).randn(5, N))
+    dc, dd, dh, dW = (np.zeros(M, np.float32) for _ in range(4))
+    hc.hc_s2_bwd(0x1F, N, M, _ptr(x), _ptr(y), _ptr(g), _ptr(xc), _ptr(yc), _ptr(h), _ptr(W),
+                 _ptr(dc), _ptr(dd), _ptr(dh), _ptr(dW))
+    g6 = np.zeros((6, N, 1)); g6[:5, :, 0] = g
+    G = cf.grads2d("softplus", x, y, xc, yc, h, W.reshape(1, -1), g6)
+    for got, key in ((dc, "d_xc"), (dd, "d_yc"), (dh, "d_h"), (dW, "d_W")):
+        assert np.isfinite(got).all()
+        assert mixed_err(got, np.asarray(G[key]).reshape(-1)) < TOL, key

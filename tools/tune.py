@@ -41,8 +41,8 @@ def main():
     pde, nn = synthetic.make_state(samples=a.samples, device="cuda")
     xs, ys = (t.detach() for t in pde.p_samples)
     N, M = xs.numel(), nn.layer1.n
-    os.environ["SPINN_TUNE"] = "fwd=0,bwd=0,waves=2"
     step = PoissonInteriorStep(nn, xs, ys, structured=a.mask != 0)
+    step.lib.spinn_set_tuning(b"fwd=0,bwd=0,waves=2")
     ref = step.run(all_reduce=False).clone()
     ref_jets = step.jets.clone()
     lib, P = step.lib, (lambda t: None if t is None else t.data_ptr())
@@ -63,14 +63,14 @@ def main():
 
     print(f"N={N} M={M}")
     for v in [int(t) for t in a.fwd.split(",") if t]:
-        os.environ["SPINN_TUNE"] = f"fwd={v},bwd=0,waves=2"
+        lib.spinn_set_tuning(f"fwd={v},bwd=0,waves=2".encode())
         step.jets.zero_()
         ms = time_ms(fwd)
         err = float((step.jets - ref_jets).abs().max() / ref_jets.abs().max())
         print(f"fwd variant {v}: {ms:8.3f} ms   {N * M * 23 / ms / 1e9:7.2f} TFLOP/s   maxdiff {err:.2e}", flush=True)
     for v in [int(t) for t in a.bwd.split(",") if t]:
         for w in [int(t) for t in a.waves.split(",") if t]:
-            os.environ["SPINN_TUNE"] = f"fwd=0,bwd={v},waves={w}"
+            lib.spinn_set_tuning(f"fwd=0,bwd={v},waves={w}".encode())
             step.pack.flat.zero_()
             ms = time_ms(bwd)
             n = step.pack.slices["loss"][0]
