@@ -367,6 +367,7 @@ def run_ours(args):
                                   P(p.view("d_b")), P(step.ws_b), step.ws_b.numel(), S())
         assert rc == 0
 
+    step.run(all_reduce=False, separate=True)       # leaves dLoss/dJets in step.gjets for the per-kernel timing
     ms_fwd = max_over_ranks(time_call(fwd_only))
     ms_bwd = max_over_ranks(time_call(bwd_only))
     pairs_loc = float(n_loc) * M
@@ -731,7 +732,8 @@ def run_ours(args):
                    "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
                                  if ws > 1 else "none (1 GPU)"},
         "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (PoissonInteriorStep.LAUNCHES + int(args.general_backward)) * args.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (PoissonInteriorStep.LAUNCHES_SEPARATE if args.general_backward
+                                                        else PoissonInteriorStep.LAUNCHES) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "general_upstream": general,
         "compact_support_opt_in": compact,
         "reference_algorithm_on_this_gpu": gpu_eager,

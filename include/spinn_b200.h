@@ -115,6 +115,25 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
                              size_t workspace_bytes, void* stream);
 size_t spinn2d_poisson_residual_workspace_bytes(int N);
 
+/* ---- the whole interior step of the stock Poisson residual in ONE call (K = 1):
+ * what RegularPDE.interior_loss + loss.backward() compute (pde2d_base.py:132-141, common.py:242-248)
+ * for res = scale*(u_xx + u_yy + amp*sin(kx x) sin(ky y) + f0), loss = sum(res^2)/n_total.
+ * Five launches: node constants of both passes, forward jets, residual epilogue writing the
+ * backward's point-pair records directly (the upstream gradient never exists as an [5][N] array),
+ * structured backward, second stage (gradients + loss).  jets [5][N] and *loss are overwritten;
+ * gradients as in spinn2d_jets_bwd (d_bias, if given, receives 0: the residual does not depend on u).
+ * ws_fwd / ws_bwd: sized by spinn2d_fwd_workspace_bytes / spinn2d_bwd_workspace_bytes. */
+int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, int M_fixed,
+                                  const float* x, const float* y,
+                                  const float* xc_free, const float* yc_free,
+                                  const float* xc_fixed, const float* yc_fixed,
+                                  const float* h, int h_is_scalar, const float* W, const float* bias,
+                                  float scale, float amp, float kx, float ky, float f0,
+                                  float* jets, float* loss,
+                                  float* d_xc, float* d_yc, float* d_h, float* d_W, float* d_bias,
+                                  void* ws_fwd, size_t ws_fwd_bytes, void* ws_bwd, size_t ws_bwd_bytes,
+                                  void* stream);
+
 /* ---- compact-support ("cut-off") evaluation, 2-D Gaussian kernel, K = 1  (OPT-IN; SURVEY 8f-4,
  * manuscript :1089-1095).  Same per-pair formulas as the dense calls, but (32-node block) x
  * (64-point group) combinations whose bounding boxes are farther apart than cutoff * h_max are

@@ -890,6 +890,7 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
 // second stage: bias gradient partials, chunk reduction, scalar-h reduction
 // -----------------------------------------------------------------------------
 constexpr int BIAS_BLOCKS = 1024;
+constexpr int LOSS_BLOCKS = 1024;
 
 __global__ void __launch_bounds__(256)
 bias_partial_kernel(int N, int K, const float* __restrict__ g0, float* __restrict__ bpart) {
@@ -920,11 +921,28 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(int dim, int K, int M, int Mfree, int Mp, int C, const float* __restrict__ partials,
                 const float* __restrict__ bpart, int nb, float* __restrict__ d_xc,
                 float* __restrict__ d_yc, float* __restrict__ d_h, float* __restrict__ d_W,
-                float* __restrict__ d_bias) {
+                float* __restrict__ d_bias, const float* __restrict__ lpart, int nlp,
+                float* __restrict__ loss) {
   __shared__ double red[8][33];
   const int nacc = dim + 1 + K;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int a = blockIdx.y;
+  if (a == nacc + 1) {                   // loss row (fused interior step): loss = sum of block partials
+    if (blockIdx.x != 0 || loss == nullptr) return;
+    const int t = ty * 32 + tx;
+    double s = 0.0;
+    for (int b = t; b < nlp; b += 256) s += (double)lpart[b];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+      double v = 0.0;
+      for (int r = 0; r < 8; ++r) v += red[r][tx];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (tx == 0) loss[0] = (float)v;
+    }
+    return;
+  }
   if (a == nacc) {                       // bias row
     if (blockIdx.x != 0 || d_bias == nullptr) return;
     const int t = ty * 32 + tx;
@@ -1021,6 +1039,104 @@ add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ o
 }
 
 // -----------------------------------------------------------------------------
+// Fused interior step (stock Poisson residual): node packing for BOTH passes in one kernel, and the
+// residual epilogue that writes the backward's point-pair records directly (no gjets round trip).
+// -----------------------------------------------------------------------------
+template <int KIND>
+__global__ void pack_nodes_step_kernel(int M, int Mfree, int npairs, int Mp,
+                                       const float* __restrict__ xf, const float* __restrict__ yf,
+                                       const float* __restrict__ xfix, const float* __restrict__ yfix,
+                                       const float* __restrict__ h, int hs, const float* __restrict__ W,
+                                       float4* __restrict__ recs, float* __restrict__ soa) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  auto node = [&](int j, float& c, float& d, float& hh, float& w) {
+    c = 0.f; d = 0.f; hh = 1.f; w = 0.f;
+    if (j < M) {
+      c = j < Mfree ? xf[j] : xfix[j - Mfree];
+      d = j < Mfree ? yf[j] : yfix[j - Mfree];
+      hh = hs ? h[0] : h[j];
+      w = W[j];
+    }
+  };
+  if (t < npairs) {                      // forward record of node pair t
+    float v[2][6];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      float c, d, hh, w;
+      node(2 * t + l, c, d, hh, w);
+      if (KIND == GAUSSIAN) {
+        const G2FwdNode n = g2_fwd_node(c, d, hh, w);
+        v[l][0] = n.nc; v[l][1] = n.nd; v[l][2] = n.rp; v[l][3] = n.w0; v[l][4] = n.w1; v[l][5] = n.w2;
+      } else {
+        const S2FwdNode n = s2_fwd_node(c, d, hh, w);
+        v[l][0] = n.nc; v[l][1] = n.nd; v[l][2] = n.c1; v[l][3] = n.w0; v[l][4] = n.w1; v[l][5] = n.w2;
+      }
+    }
+    recs[3 * (size_t)t + 0] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+    recs[3 * (size_t)t + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+    recs[3 * (size_t)t + 2] = make_float4(v[0][4], v[1][4], v[0][5], v[1][5]);
+  }
+  if (t < Mp) {                          // backward SoA column t: c, d, h, 1/h, W
+    float c, d, hh, w;
+    node(t, c, d, hh, w);
+    soa[t] = c;
+    soa[(size_t)Mp + t] = d;
+    soa[2 * (size_t)Mp + t] = hh;
+    soa[3 * (size_t)Mp + t] = 1.0f / hh;
+    soa[4 * (size_t)Mp + t] = w;
+  }
+}
+
+// res = scale (u_xx + u_yy + f),  f = amp sin(kx x) sin(ky y) + f0;  loss partial = sum res^2 / n_total;
+// dLoss/du_xx = dLoss/du_yy = g = 2 scale res / n_total  ->  the point-pair record of the backward:
+//   LAPL (Gaussian, g2_lapl_point):   {x,x',y,y'} {D,D',g4,g4'} {m,m',k3,k3'} {k4,k4',0,0}
+//   general layout (softplus-hat):    {x,x',y,y'} {0,0,0,0} {0,0,g,g'} {g,g',0,0}
+template <bool LAPL>
+__global__ void __launch_bounds__(256)
+poisson_residual_pack_kernel(int N, int N2, float inv_n, const float* __restrict__ x,
+                             const float* __restrict__ y, const float* __restrict__ jets, float scale,
+                             float amp, float kx, float ky, float f0, float4* __restrict__ recs,
+                             float* __restrict__ lpart) {
+  __shared__ float red[8];
+  const size_t n = (size_t)N;
+  float s = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N2; p += gridDim.x * blockDim.x) {
+    const int i0 = 2 * p, i1 = 2 * p + 1;
+    const bool v1 = i1 < N;
+    // scalar loads: a warp still covers 256 contiguous bytes per array, and no alignment is assumed
+    const float xa = x[i0], ya = y[i0], la = jets[3 * n + i0] + jets[4 * n + i0];
+    const float xb = v1 ? x[i1] : xa, yb = v1 ? y[i1] : ya;
+    const float lb = v1 ? jets[3 * n + i1] + jets[4 * n + i1] : 0.f;
+    const float ra = scale * (la + fmaf(amp * sinf(kx * xa), sinf(ky * ya), f0));
+    const float rb = v1 ? scale * (lb + fmaf(amp * sinf(kx * xb), sinf(ky * yb), f0)) : 0.f;
+    s = fmaf(ra, ra, s);
+    s = fmaf(rb, rb, s);
+    const float ga = 2.f * scale * ra * inv_n, gb = 2.f * scale * rb * inv_n;
+    float4* r = recs + 4 * (size_t)p;
+    r[0] = make_float4(xa, xb, ya, yb);
+    if (LAPL) {
+      const G2LaplPoint ca = g2_lapl_point(ga, ga), cb = g2_lapl_point(gb, gb);
+      r[1] = make_float4(ca.D, cb.D, ca.g4, cb.g4);
+      r[2] = make_float4(ca.m, cb.m, ca.k3, cb.k3);
+      r[3] = make_float4(ca.k4, cb.k4, 0.f, 0.f);
+    } else {
+      r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      r[2] = make_float4(0.f, 0.f, ga, gb);
+      r[3] = make_float4(ga, gb, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    lpart[blockIdx.x] = v * inv_n;
+  }
+}
+
+// -----------------------------------------------------------------------------
 // fast forward launcher (one instantiation per kernel kind / tile shape)
 // -----------------------------------------------------------------------------
 struct FastFwdArgs {
@@ -1090,7 +1206,7 @@ struct BwdPlan {
   int per_chunk;       // points (generic) or point pairs (fast) per chunk
   int N2;              // fast: point pairs
   int variant;         // fast: BWD_CFGS index
-  size_t off_soa, off_pts, off_part, off_bias, off_htmp, ws_bytes;
+  size_t off_soa, off_pts, off_part, off_bias, off_htmp, off_loss, ws_bytes;
 };
 
 static bool bwd_is_fast(int dim, int kind, int level, int K) {
@@ -1197,6 +1313,7 @@ static BwdPlan plan_bwd(int dim, int kind, int level, int N, int M, int K, bool 
   p.off_part = off; off += align_up(part_floats * sizeof(float), 256);
   p.off_bias = off; off += align_up((size_t)BIAS_BLOCKS * SPINN_MAX_K * sizeof(float), 256);
   p.off_htmp = off; off += align_up(Mp_w * sizeof(float), 256);
+  p.off_loss = off; off += align_up((size_t)LOSS_BLOCKS * sizeof(float), 256);
   p.ws_bytes = off;
   return p;
 }
@@ -1279,7 +1396,7 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
                          const float* x, const float* y, const float* xf, const float* yf,
                          const float* xfix, const float* yfix, const float* h, int hs,
                          const float* W, const float* bias, float* jets, void* ws, size_t ws_bytes,
-                         void* stream) {
+                         void* stream, bool nodes_packed = false) {
   int rc = check_common(dim, kind, level, N, M_free, M_fixed, K);
   if (rc) return rc;
   if (N == 0) return SPINN_OK;
@@ -1294,7 +1411,8 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
 
   if (p.fast) {
     float4* recs = (float4*)ws;
-    if (kind == SPINN_KIND_GAUSSIAN)
+    if (nodes_packed) {
+    } else if (kind == SPINN_KIND_GAUSSIAN)
       pack_nodes_k1fwd_kernel<GAUSSIAN><<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
                                                                                   xfix, yfix, h, hs, W, recs);
     else
@@ -1343,18 +1461,23 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
   return SPINN_OK;
 }
 
+// fused interior step: nodes and point records are already in the workspace, and the second stage
+// also reduces the loss partials
+struct BwdFused { int nlp; float* loss; };
+
 static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, int M_free,
                          int M_fixed, int K, const float* x, const float* y, const float* xf, const float* yf,
                          const float* xfix, const float* yfix, const float* h, int hs,
                          const float* W, const float* gj, float* d_xc, float* d_yc, float* d_h,
-                         float* d_W, float* d_bias, void* ws, size_t ws_bytes, void* stream) {
+                         float* d_W, float* d_bias, void* ws, size_t ws_bytes, void* stream,
+                         const BwdFused* fused = nullptr) {
   int rc = check_common(dim, kind, level, N, M_free, M_fixed, K);
   if (rc) return rc;
   const int M = M_free + M_fixed;
   if (!h || !W || !d_h || !d_W || (M_free && (!xf || !d_xc)) || (M_fixed && !xfix) ||
       (dim == 2 && ((M_free && (!yf || !d_yc)) || (M_fixed && !yfix))))
     return fail(SPINN_E_BADARG, "null pointer argument in jets_bwd");
-  if (N > 0 && (!x || (dim == 2 && !y) || !gj))
+  if (N > 0 && !fused && (!x || (dim == 2 && !y) || !gj))
     return fail(SPINN_E_BADARG, "null point/gradient pointer in jets_bwd");
   cudaStream_t s = (cudaStream_t)stream;
   if (present_mask < 0) return fail(SPINN_E_BADARG, "present_mask must be >= 0");
@@ -1379,7 +1502,8 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
     return SPINN_OK;
   }
 
-  if (dim == 2)
+  if (fused) {
+  } else if (dim == 2)
     pack_nodes_soa_kernel<2><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, yf, xfix, yfix, h, hs, W, soa);
   else
     pack_nodes_soa_kernel<1><<<ceil_div_i(p.Mp, 128), 128, 0, s>>>(M, M_free, p.Mp, K, xf, nullptr, xfix, nullptr, h, hs, W, soa);
@@ -1389,7 +1513,7 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
   if (p.fast && kind == SPINN_KIND_SOFTPLUS) {
     float4* ptrecs = (float4*)(base + p.off_pts);
     const int pgrid = ceil_div_i(p.N2, 256);
-    pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    if (!fused) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     LAUNCH_CHECK("pack_points_g2bwd_kernel");
     const int sm = (mask == 0x01) ? 0x01 : ((mask & ~0x18) == 0 ? 0x18 : 0x1F);
 #define SPINN_LAUNCH_S2_BWD(Q_, T_, B_, TILE_)                                                                 \
@@ -1413,7 +1537,8 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
     float4* ptrecs = (float4*)(base + p.off_pts);
     const int mode = bwd_mode_for(mask);
     const int pgrid = ceil_div_i(p.N2, 256);
-    if (bwd_general(mode)) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
+    if (fused) { }
+    else if (bwd_general(mode)) pack_points_g2bwd_kernel<BWD_ALL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     else if (mode == BWD_LAPL) pack_points_g2bwd_kernel<BWD_LAPL><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     else pack_points_g2bwd_kernel<BWD_U><<<pgrid, 256, 0, s>>>(N, p.N2, x, y, gj, mask, ptrecs);
     LAUNCH_CHECK("pack_points_g2bwd_kernel");
@@ -1460,8 +1585,9 @@ static int jets_bwd_impl(int dim, int kind, int level, int present_mask, int N, 
     bias_partial_kernel<<<nb, 256, 0, s>>>(N, K, gj, bpart);
     LAUNCH_CHECK("bias_partial_kernel");
   }
-  finalize_kernel<<<dim3(ceil_div_i(M, 32), nacc + 1), dim3(32, 8), 0, s>>>(dim, K, M, M_free, p.Mp, p.chunks, partials, bpart,
-                                                     nb, d_xc, d_yc, hs ? htmp : d_h, d_W, d_bias);
+  finalize_kernel<<<dim3(ceil_div_i(M, 32), nacc + (fused ? 2 : 1)), dim3(32, 8), 0, s>>>(
+      dim, K, M, M_free, p.Mp, p.chunks, partials, bpart, nb, d_xc, d_yc, hs ? htmp : d_h, d_W, d_bias,
+      fused ? (const float*)(base + p.off_loss) : nullptr, fused ? fused->nlp : 0, fused ? fused->loss : nullptr);
   LAUNCH_CHECK("finalize_kernel");
   if (hs) {
     sum_to_scalar_kernel<<<1, 256, 0, s>>>(M, htmp, d_h);
@@ -1557,6 +1683,60 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
   add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
   LAUNCH_CHECK("add_partials_kernel");
   return SPINN_OK;
+}
+
+int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, int M_fixed, const float* x,
+                                  const float* y, const float* xc_free, const float* yc_free,
+                                  const float* xc_fixed, const float* yc_fixed, const float* h,
+                                  int h_is_scalar, const float* W, const float* bias, float scale, float amp,
+                                  float kx, float ky, float f0, float* jets, float* loss, float* d_xc,
+                                  float* d_yc, float* d_h, float* d_W, float* d_bias, void* ws_fwd,
+                                  size_t ws_fwd_bytes, void* ws_bwd, size_t ws_bwd_bytes, void* stream) {
+  int rc = check_common(2, kind, 2, N, M_free, M_fixed, 1);
+  if (rc) return rc;
+  if (N <= 0 || n_total <= 0.0) return fail(SPINN_E_BADARG, "interior step needs N > 0 and n_total > 0");
+  if (!x || !y || !jets || !loss || !h || !W || !d_h || !d_W || (M_free && (!xc_free || !yc_free || !d_xc || !d_yc)) ||
+      (M_fixed && (!xc_fixed || !yc_fixed)))
+    return fail(SPINN_E_BADARG, "null pointer argument in poisson_interior_step");
+  const int M = M_free + M_fixed;
+  cudaStream_t s = (cudaStream_t)stream;
+  const FwdPlan fp = plan_fwd(2, kind, 2, M, 1);
+  const BwdPlan bp = plan_bwd(2, kind, 2, N, M, 1, false, BWD_LAPL);
+  if (!ws_fwd || ws_fwd_bytes < fp.ws_bytes || !ws_bwd || ws_bwd_bytes < bp.ws_bytes)
+    return fail(SPINN_E_WORKSPACE, "interior step workspace too small (fwd %zu < %zu or bwd %zu < %zu)",
+                ws_fwd_bytes, fp.ws_bytes, ws_bwd_bytes, bp.ws_bytes);
+  char* bb = (char*)ws_bwd;
+  // 1. node constants of both passes
+  const int nthreads = fp.npairs > bp.Mp ? fp.npairs : bp.Mp;
+  if (kind == SPINN_KIND_GAUSSIAN)
+    pack_nodes_step_kernel<GAUSSIAN><<<ceil_div_i(nthreads, 128), 128, 0, s>>>(
+        M, M_free, fp.npairs, bp.Mp, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar, W, (float4*)ws_fwd,
+        (float*)(bb + bp.off_soa));
+  else
+    pack_nodes_step_kernel<SOFTPLUS><<<ceil_div_i(nthreads, 128), 128, 0, s>>>(
+        M, M_free, fp.npairs, bp.Mp, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar, W, (float4*)ws_fwd,
+        (float*)(bb + bp.off_soa));
+  LAUNCH_CHECK("pack_nodes_step_kernel");
+  // 2. forward jets
+  rc = jets_fwd_impl(2, kind, 2, N, M_free, M_fixed, 1, x, y, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar,
+                     W, bias, jets, ws_fwd, ws_fwd_bytes, stream, true);
+  if (rc) return rc;
+  // 3. residual, loss partials, point-pair records of the backward
+  const int N2 = (N + 1) / 2;
+  int blocks = ceil_div_i(N2, 256 * 2);
+  if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+  const float inv_n = (float)(1.0 / n_total);
+  if (kind == SPINN_KIND_GAUSSIAN)
+    poisson_residual_pack_kernel<true><<<blocks, 256, 0, s>>>(N, N2, inv_n, x, y, jets, scale, amp, kx, ky, f0,
+                                                              (float4*)(bb + bp.off_pts), (float*)(bb + bp.off_loss));
+  else
+    poisson_residual_pack_kernel<false><<<blocks, 256, 0, s>>>(N, N2, inv_n, x, y, jets, scale, amp, kx, ky, f0,
+                                                               (float4*)(bb + bp.off_pts), (float*)(bb + bp.off_loss));
+  LAUNCH_CHECK("poisson_residual_pack_kernel");
+  // 4.-5. backward on the packed records + second stage (gradients, bias gradient = 0, loss)
+  const BwdFused fused = {blocks, loss};
+  return jets_bwd_impl(2, kind, 2, 0x18, N, M_free, M_fixed, 1, x, y, xc_free, yc_free, xc_fixed, yc_fixed, h,
+                       h_is_scalar, W, nullptr, d_xc, d_yc, d_h, d_W, d_bias, ws_bwd, ws_bwd_bytes, stream, &fused);
 }
 
 }  // extern "C"

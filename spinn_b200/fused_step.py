@@ -20,10 +20,12 @@ UNIT_SOURCE = dict(scale=1.0, amp=0.0, kx=0.0, ky=0.0, f0=1.0)
 
 
 class PoissonInteriorStep:
-    #: kernels of ours enqueued by one run(): pack_nodes(fwd), fwd, residual, add_partials,
-    #: pack_nodes(bwd), pack_points, bwd, finalize  (+ bias_partial when u itself has an upstream
-    #: gradient, i.e. structured=False)
-    LAUNCHES = 8
+    #: kernels of ours enqueued by one run() through spinn2d_poisson_interior_step: pack_nodes_step,
+    #: forward, residual epilogue (writes the backward's point records), backward, second stage.
+    #: structured=False / cutoff take the separate calls: pack_nodes(fwd), fwd, residual,
+    #: add_partials, pack_nodes(bwd), pack_points, bwd, bias_partial, finalize
+    LAUNCHES = 5
+    LAUNCHES_SEPARATE = 9
 
     def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True, cutoff=None):
         if nn.layer2.weight.shape[0] != 1:
@@ -57,17 +59,33 @@ class PoissonInteriorStep:
             self.ws_sf = torch.empty(self.lib.spinn2d_sparse_fwd_workspace_bytes(self.N, M), dtype=torch.uint8, device=dev)
             self.ws_sb = torch.empty(self.lib.spinn2d_sparse_bwd_workspace_bytes(self.N, M), dtype=torch.uint8, device=dev)
 
-    def run(self, all_reduce=True):
+    def run(self, all_reduce=True, separate=False):
         """Enqueue one interior fwd+bwd on the current stream.  Afterwards
-        ``self.pack.flat`` holds [grads | loss] (summed over ranks if all_reduce)."""
+        ``self.pack.flat`` holds [grads | loss] (summed over ranks if all_reduce).
+        separate=True issues the three C-ABI calls (forward, residual, backward) one by one and
+        leaves dLoss/dJets in ``self.gjets``; the default is the single fused entry."""
         lib, nn = self.lib, self.nn
         l1, l2 = nn.layer1, nn.layer2
         s = _stream()
         hs = int(l1.h.numel() == 1)
         p = self.pack
-        p.view("loss").zero_()
         if self.cutoff:
+            p.view("loss").zero_()
             return self._run_sparse(all_reduce)
+        if self.upstream_mask == 0x18 and not separate:
+            r = self.res
+            rc = lib.spinn2d_poisson_interior_step(
+                nn.kind, self.N, self.n_total, self.Mf, self.Mx, _ptr(self.x), _ptr(self.y), _ptr(l1.x), _ptr(l1.y),
+                _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs, _ptr(l2.weight), _ptr(l2.bias), r["scale"], r["amp"],
+                r["kx"], r["ky"], r["f0"], _ptr(self.jets), _ptr(p.view("loss")), _ptr(p.view("d_x")),
+                _ptr(p.view("d_y")), _ptr(p.view("d_h")), _ptr(p.view("d_W")),
+                _ptr(p.view("d_b")) if p.has("d_b") else None, _ptr(self.ws_f), self.ws_f.numel(),
+                _ptr(self.ws_b), self.ws_b.numel(), s)
+            _cabi.check(rc, "spinn2d_poisson_interior_step")
+            if all_reduce:
+                p.all_reduce()
+            return p.flat
+        p.view("loss").zero_()
         rc = lib.spinn2d_jets_fwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(self.y),
                                   _ptr(l1.x), _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs,
                                   _ptr(l2.weight), _ptr(l2.bias), _ptr(self.jets), _ptr(self.ws_f),
@@ -88,6 +106,16 @@ class PoissonInteriorStep:
         if all_reduce:
             p.all_reduce()
         return p.flat
+
+    def upstream_from_jets(self):
+        """dLoss/dJets [5][N] recomputed from ``self.jets`` with plain torch ops (for checks: the fused
+        entry never materialises it)."""
+        r = self.res
+        f = r["amp"] * torch.sin(r["kx"] * self.x) * torch.sin(r["ky"] * self.y) + r["f0"]
+        res = r["scale"] * (self.jets[3] + self.jets[4] + f)
+        g = torch.zeros_like(self.jets)
+        g[3] = g[4] = (2.0 * r["scale"] / self.n_total) * res
+        return g
 
     def _run_sparse(self, all_reduce):
         lib, nn, p, s = self.lib, self.nn, self.pack, _stream()

@@ -244,7 +244,7 @@ def test_full_size_backward_sampled_nodes_vs_oracle(full_state):
     # oracle on a subset of NODES over a subset of POINTS is not a valid check of a sum over all
     # points, so: all 4M points, 6 nodes, fp64, chunked (gradients of node j depend on node j only
     # once the upstream g = dLoss/dJets is given).
-    g = step.gjets.cpu().numpy().astype(np.float64)[:, :, None]            # (5, N, 1)
+    g = step.upstream_from_jets().cpu().numpy().astype(np.float64)[:, :, None]            # (5, N, 1)
     x, y = xs.cpu().numpy(), ys.cpu().numpy()
     xc, yc = (t.detach().cpu().numpy() for t in l1.centers())
     h, W = l1.h.detach().cpu().numpy(), l2.weight.detach().cpu().numpy()
@@ -267,6 +267,28 @@ def test_full_size_backward_sampled_nodes_vs_oracle(full_state):
     # determinism: no atomics anywhere -> bit-identical repeat
     flat2 = step.run(all_reduce=False)
     assert torch.equal(flat, flat2)
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "softplus"])
+@pytest.mark.parametrize("samples,nodes,b_nodes", [(40000, 400, 20), (1000 * 1000 + 1, 900, 31), (169, 25, 5)])
+def test_fused_interior_step_equals_the_separate_calls(kind, samples, nodes, b_nodes):
+    """spinn2d_poisson_interior_step (5 launches, no dLoss/dJets array) against forward + residual
+    + backward issued one by one: same jets, bit-identical gradients, same loss; odd point counts."""
+    from spinn_b200 import synthetic
+    from spinn_b200.fused_step import PoissonInteriorStep
+    pde, nn = synthetic.make_state(nodes=nodes, b_nodes=b_nodes, samples=samples, kind=kind, device="cuda", seed=11)
+    xs, ys = (t.detach() for t in pde.p_samples)
+    if samples % 2:                                    # odd N: drop to an odd count
+        xs, ys = xs[:samples].contiguous(), ys[:samples].contiguous()
+    step = PoissonInteriorStep(nn, xs, ys)
+    nl = step.pack.slices["loss"][0]
+    a = step.run(all_reduce=False).clone()
+    jets_a = step.jets.clone()
+    b = step.run(all_reduce=False, separate=True).clone()
+    assert torch.equal(jets_a, step.jets)
+    assert torch.equal(a[:nl], b[:nl])
+    assert abs(float(a[nl]) - float(b[nl])) <= 2e-6 * abs(float(b[nl]))
+    assert torch.allclose(step.gjets[3], step.upstream_from_jets()[3], rtol=1e-5, atol=0)
 
 
 def test_full_size_point_sharding_is_additive(full_state):
@@ -310,7 +332,7 @@ def test_beyond_baseline_size_16m_points_16384_nodes():
     del jets
     step = PoissonInteriorStep(nn, xs, ys)
     flat = step.run(all_reduce=False).clone()
-    g = step.gjets.cpu().numpy().astype(np.float64)[:, :, None]
+    g = step.upstream_from_jets().cpu().numpy().astype(np.float64)[:, :, None]
     nodes = np.array([0, 15375, 15376, 16383])
     G = cf.grads2d("gaussian", xs.cpu().numpy(), ys.cpu().numpy(), xc[nodes], yc[nodes], h[nodes], W[:, nodes], g,
                    chunk=262144)

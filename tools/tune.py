@@ -43,7 +43,7 @@ def main():
     N, M = xs.numel(), nn.layer1.n
     step = PoissonInteriorStep(nn, xs, ys, structured=a.mask != 0)
     step.lib.spinn_set_tuning(b"fwd=0,bwd=0,waves=2")
-    ref = step.run(all_reduce=False).clone()
+    ref = step.run(all_reduce=False, separate=True).clone()
     ref_jets = step.jets.clone()
     lib, P = step.lib, (lambda t: None if t is None else t.data_ptr())
     l1, l2 = nn.layer1, nn.layer2
