@@ -130,6 +130,33 @@ def shard_interior(pde, rank=None, world_size=None):
     return pde
 
 
+def shard_boundary(pde, rank=None, world_size=None, min_per_rank=32):
+    """Shard the boundary points like the interior when the problem class says its
+    boundary penalty is a plain SUM over boundary points (`boundary_reduction = "sum"`, e.g. the
+    Dirichlet penalties of the Poisson configs) and keeps them in `b_samples`.  Returns True if the
+    boundary is now sharded (local sums then add up across ranks), False if every rank keeps all of
+    it.  Cached boundary targets are dropped so that they are rebuilt for the slice."""
+    if rank is None:
+        rank, world_size, _ = world()
+    if world_size == 1 or getattr(pde, "boundary_reduction", None) != "sum":
+        return False
+    if getattr(pde, "_bshard", None) == (rank, world_size):
+        return True
+    pts = getattr(pde, "b_samples", None)
+    if pts is None or torch.is_tensor(pts) or len(pts) == 0:
+        return False
+    n = pts[0].numel()
+    if n < min_per_rank * world_size:
+        return False
+    lo, hi = shard_range(n, rank, world_size)
+    pde.b_samples = tuple(t.detach()[lo:hi].clone().requires_grad_(t.requires_grad) for t in pts)
+    for cached in ("_ub", "_ub_dev"):
+        if hasattr(pde, cached):
+            setattr(pde, cached, None)
+    pde._bshard = (rank, world_size)
+    return True
+
+
 def all_reduce_gradients(params, average=True, buf=None):
     """ONE collective for all parameter gradients: pack -> all_reduce -> unpack."""
     params = [p for p in params if p.grad is not None]

@@ -35,13 +35,9 @@ class GraphedOptimizer(DistributedOptimizer):
         # never-zeroed) .grad on the sample tensors (pde2d_base.py:91); skipping that saves kernels
         # and keeps those buffers from growing without bound over long graphed runs
         loss.backward(retain_graph=True, inputs=self._params)
-        if self.world > 1:
-            import torch.distributed as dist
-            self._buf = distributed.all_reduce_gradients(list(self.nn.parameters()), average=False,
-                                                         buf=self._buf)
-            loss = loss.detach().clone()
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
-        return loss
+        # gradients accumulate in place into views of one flat buffer whose last slot takes the loss:
+        # ONE all-reduce per step (captured inside the graph when WORLD_SIZE > 1)
+        return self.reduce_step(loss)
 
     def _pre_step(self):
         hook = getattr(self.pde, "graph_pre_step", None)
@@ -76,17 +72,18 @@ class GraphedOptimizer(DistributedOptimizer):
         with torch.cuda.stream(side):
             for i in range(n_eager):
                 self._pre_step()
-                self.opt.zero_grad(set_to_none=True)
+                self.bind_gradients().zero_()
                 loss = self._body()
                 self.opt.step()
                 loss_buf[i].copy_(loss.detach())
         torch.cuda.current_stream().wait_stream(side)
 
         if graph is None and n_train > n_eager:
-            self.opt.zero_grad(set_to_none=True)
             self._pre_step_capture = True
+            flat = self.bind_gradients()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
+                flat.zero_()
                 static_loss = self._body()
                 self.opt.step()
             self._captured = (graph, static_loss)

@@ -287,10 +287,12 @@ class _Attach(torch.autograd.Function):
         vx, vy = ctx.saved_tensors
 
         def along(v):                # sum_k g * v; a derivative declared "not provided" reads as zero
-            if v is None:
-                return torch.zeros_like(g if g.dim() == 1 else g[..., 0])
+            if v is None:            # (a broadcast scalar zero: no fill kernel over N elements)
+                return g.new_zeros(()).expand(g.shape[0])
             t = g * v
-            return t.sum(-1) if t.dim() > 1 else t
+            if t.dim() == 1:
+                return t
+            return t.squeeze(-1) if t.shape[-1] == 1 else t.sum(-1)      # K = 1: a view, no reduction
 
         gx = along(vx)
         gy = along(vy) if ctx.has_y else None
@@ -324,7 +326,7 @@ class _Attach1(torch.autograd.Function):
         (vx,) = ctx.saved_tensors
         gx = g * vx
         if gx.dim() > 1:
-            gx = gx.sum(-1)
+            gx = gx.squeeze(-1) if gx.shape[-1] == 1 else gx.sum(-1)
         return g, gx, None
 
 

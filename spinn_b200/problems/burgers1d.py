@@ -24,6 +24,9 @@ def initial_profile(ic, x, t, a=0.0):
 
 
 class Burgers1D(IBVP2D):
+    #: the boundary penalty is a plain sum over boundary points -> they can be sharded across ranks
+    boundary_reduction = "sum"
+
     EXTRA_FLAGS = (
         (("--viscosity",), "viscosity", 0.0, float, "Viscosity in viscous Burgers equation."),
         (("--ic",), "ic", "gaussian", ("jump", "gaussian", "sin", "sin2"),

@@ -11,6 +11,9 @@ from .ibvp2d_base import IBVP2D
 
 
 class Heat1D(IBVP2D):
+    #: the boundary penalty is a plain sum over boundary points -> they can be sharded across ranks
+    boundary_reduction = "sum"
+
     C = 1.0
     B1 = 2.0
 

@@ -14,6 +14,9 @@ PI = np.pi
 
 
 class Poisson2D(RegularPDE):
+    #: the boundary penalty is a plain sum over boundary points -> they can be sharded across ranks
+    boundary_reduction = "sum"
+
     def pde(self, x, y, u, ux, uy, uxx, uyy):
         f = 20 * PI ** 2 * torch.sin(2 * PI * x) * torch.sin(4 * PI * y)
         return 0.1 * (uxx + uyy + f)

@@ -91,12 +91,26 @@ def _train_worker(rank, world, port, out_path, steps):
     np.random.seed(0)
     torch.manual_seed(0)
     app = poisson2d_sine.make_app()
+    calls = {"n": 0}
+    real_all_reduce = dist.all_reduce
+
+    def counting_all_reduce(*a, **k):
+        calls["n"] += 1
+        return real_all_reduce(*a, **k)
+    dist.all_reduce = counting_all_reduce
     with contextlib.redirect_stdout(io.StringIO()):
         app.run(args=["--nodes", "100", "--samples", "400", "--n-train", str(steps), "--lr", "1e-3",
                       "--tol", "1e-30"])
+    dist.all_reduce = real_all_reduce
     from spinn_b200.dist_optimizer import DistributedOptimizer
     assert isinstance(app.solver, DistributedOptimizer)
     assert app.pde.p_samples[0].numel() == 400 // world
+    # boundary ring (76 points) sharded like the interior; ONE collective per closure, gradients are
+    # views of the reduced buffer (no pack / unpack)
+    assert app.solver.boundary_sharded and app.pde.b_samples[0].numel() == 76 // world
+    assert calls["n"] == steps, (calls, steps)
+    flat = app.solver._flat
+    assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in app.nn.parameters())
     if rank == 0:
         np.save(out_path, np.asarray(app.solver.loss))
     dist.barrier()
