@@ -223,7 +223,7 @@ struct FwdCfg { int p, threads, minb, unroll; };
 struct BwdCfg { int q, threads, minb, tile; };
 static const FwdCfg FWD_CFGS[] = {
     {4, 256, 2, 2},   // 0
-    {2, 512, 2, 2},   // 1
+    {2, 256, 2, 4},   // 1  (alias of 3)
     {1, 512, 2, 4},   // 2
     {2, 256, 2, 4},   // 3  (default: best on B200 at 4M and 512K points, tools/tune.py)
 };
@@ -361,15 +361,41 @@ __device__ __forceinline__ void k1_fwd_inner(const float4* __restrict__ sm4, int
   }
 }
 
+// Residual epilogue of the stock Poisson residual, run by the forward kernel on the jets it has just
+// formed: res = scale (u_xx + u_yy + amp sin(kx x) sin(ky y) + f0), the loss
+// partial sum res^2 / n_total, and dLoss/du_xx = dLoss/du_yy = g = 2 scale res / n_total written
+// straight into the backward's point-pair record (layouts: poisson_residual_pack_kernel).
+struct FwdEpilogue {
+  float scale, amp, kx, ky, f0, inv_n;
+  float4* recs;          // [4 * ceil(N/2)] backward point-pair records
+  float* lpart;          // one loss partial per warp of the grid
+};
+
+template <int KIND>
+__device__ __forceinline__ void write_point_record(float4* __restrict__ r, float xa, float xb, float ya, float yb,
+                                                   float ga, float gb) {
+  r[0] = make_float4(xa, xb, ya, yb);
+  if (KIND == GAUSSIAN) {
+    const G2LaplPoint ca = g2_lapl_point(ga, ga), cb = g2_lapl_point(gb, gb);
+    r[1] = make_float4(ca.D, cb.D, ca.g4, cb.g4);
+    r[2] = make_float4(ca.m, cb.m, ca.k3, cb.k3);
+    r[3] = make_float4(ca.k4, cb.k4, 0.f, 0.f);
+  } else {
+    r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r[2] = make_float4(0.f, 0.f, ga, gb);
+    r[3] = make_float4(ga, gb, 0.f, 0.f);
+  }
+}
+
 // One span of the point set, walked in warp-tiles of 32*P consecutive points: tile `wt` of the span
 // starts at point `base + wt*32*P`; the span ends at `end`.  COOP: all warps of the CTA run the same
 // number of iterations (the multi-tile node loop has block-wide barriers).
-template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP>
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP, bool EPI>
 __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N, const float* __restrict__ x,
                                             const float* __restrict__ y, const float4* __restrict__ recs,
                                             const float4* __restrict__ sm4w, float4* __restrict__ sm4, int npairs,
                                             int tile_pairs, float b0, float* __restrict__ jets, bool vec,
-                                            long long gw, long long nwarps) {
+                                            long long gw, long long nwarps, const FwdEpilogue& ep, float& lsum) {
   constexpr int NJ = MIXED ? 6 : 5;
   const int lane = threadIdx.x & 31;
   const long long nwt = (end - base + 32 * P - 1) / (32 * P);
@@ -409,7 +435,37 @@ __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N
 #pragma unroll
         for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
         // `lim` (not N) bounds the stores of this span; the jets rows are N long
-        store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
+        if (!EPI || jets != nullptr) store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
+      }
+    }
+    if (EPI && active) {
+      float g[P];
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        const bool v = i0 + q < lim;
+        const float lap = (acc[q][3].x + acc[q][3].y) + (acc[q][4].x + acc[q][4].y);
+        const float res = v ? ep.scale * (lap + fmaf(ep.amp * sinf(ep.kx * px[q]), sinf(ep.ky * py[q]), ep.f0)) : 0.f;
+        lsum = fmaf(res, res, lsum);
+        g[q] = 2.f * ep.scale * res * ep.inv_n;
+      }
+      if (P == 1) {
+        // one point per thread: lanes (2k, 2k+1) form the pair (tile bases are multiples of 32)
+        const float xb = __shfl_down_sync(0xffffffffu, px[0], 1), yb = __shfl_down_sync(0xffffffffu, py[0], 1);
+        const float gb = __shfl_down_sync(0xffffffffu, g[0], 1);
+        if ((lane & 1) == 0 && i0 < lim) {
+          const bool v1 = i0 + 1 < lim;
+          write_point_record<KIND>(ep.recs + 4 * (size_t)(i0 >> 1), px[0], v1 ? xb : px[0], py[0], v1 ? yb : py[0],
+                                   g[0], v1 ? gb : 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < P; q += 2) {
+          if (i0 + q < lim) {
+            const bool v1 = i0 + q + 1 < lim;
+            write_point_record<KIND>(ep.recs + 4 * (size_t)((i0 + q) >> 1), px[q], v1 ? px[(q + 1) % P] : px[q], py[q],
+                                     v1 ? py[(q + 1) % P] : py[q], g[q], v1 ? g[(q + 1) % P] : 0.f);
+          }
+        }
       }
     }
   }
@@ -419,11 +475,11 @@ __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N
 // the remainder -- less than one round -- is walked with one point per thread (tiles of 32 points), so
 // that the last, partial round keeps (nearly) every warp of every SM busy at half the work instead of
 // leaving half of the warps idle (8-GPU shards: 3.46 rounds -> 3 rounds + one half-size round).
-template <int KIND, int P, bool MIXED, int THREADS, int UNROLL>
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool EPI>
 __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, const float* __restrict__ y,
                                             const float4* __restrict__ recs, int npairs, int tile_pairs,
                                             const float* __restrict__ bias, float* __restrict__ jets,
-                                            int vec_ok, float4* sm4) {
+                                            int vec_ok, float4* sm4, const FwdEpilogue& ep) {
   constexpr int WPC = THREADS / 32;
   // slot-major warp rank: warps 0-3 of every CTA first, then warps 4-7, ... so that a partial
   // round of warp-tiles is spread over all SMs / sub-partitions instead of leaving whole CTAs idle
@@ -433,6 +489,7 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
   const bool single = npairs <= tile_pairs;
   const bool vec = vec_ok != 0;
   const float b0 = bias ? bias[0] : 0.f;
+  float lsum = 0.f;                                // EPI: this thread's share of sum res^2
 
   if (single) {
     // the whole node-record table (48 B per node pair, 96 KB at M=4096) arrives by TMA bulk copies
@@ -452,34 +509,40 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
     mbar_wait(&bar, 0);
     const long long round_pts = nwarps * 32 * P;
     const long long main_end = P == 1 ? (long long)N : ((long long)N / round_pts) * round_pts;
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false>(0, main_end, N, x, y, recs, sm4, sm4, npairs, tile_pairs,
-                                                        b0, jets, vec, gw, nwarps);
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false, EPI>(0, main_end, N, x, y, recs, sm4, sm4, npairs,
+                                                             tile_pairs, b0, jets, vec, gw, nwarps, ep, lsum);
     if (P > 1 && main_end < N)
-      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
-                                                          tile_pairs, b0, jets, vec, gw, nwarps);
+      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false, EPI>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
+                                                               tile_pairs, b0, jets, vec, gw, nwarps, ep, lsum);
   } else {
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
-                                                       jets, vec, gw, nwarps);
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true, EPI>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
+                                                            jets, vec, gw, nwarps, ep, lsum);
+  }
+  if (EPI) {                                       // one loss partial per warp, every warp writes its slot
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((threadIdx.x & 31) == 0) ep.lpart[gw] = lsum * ep.inv_n;
   }
 }
 
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
+// EPI: the forward also runs the Poisson residual epilogue (FwdEpilogue) on its jets
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI>
 __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
-                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok, const FwdEpilogue ep) {
   extern __shared__ float4 sm4[];
-  k1_fwd_body<GAUSSIAN, P, MIXED, THREADS, UNROLL>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4);
+  k1_fwd_body<GAUSSIAN, P, MIXED, THREADS, UNROLL, EPI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
 }
 
 // the same persistent, TMA-staged forward with the softplus-hat pair function (spinn_math.cuh, FAST PATH 2)
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL>
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI>
 __global__ void __launch_bounds__(THREADS, MINB)
 s2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
-                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok) {
+                const float* __restrict__ bias, float* __restrict__ jets, int vec_ok, const FwdEpilogue ep) {
   extern __shared__ float4 sm4[];
-  k1_fwd_body<SOFTPLUS, P, MIXED, THREADS, UNROLL>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4);
+  k1_fwd_body<SOFTPLUS, P, MIXED, THREADS, UNROLL, EPI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
 }
 
 // -----------------------------------------------------------------------------
@@ -890,7 +953,7 @@ bwd_generic_kernel(int N, int Mp, int pts_per_chunk, const float* __restrict__ x
 // second stage: bias gradient partials, chunk reduction, scalar-h reduction
 // -----------------------------------------------------------------------------
 constexpr int BIAS_BLOCKS = 1024;
-constexpr int LOSS_BLOCKS = 1024;
+constexpr int LOSS_BLOCKS = 8192;   // >= warps of the largest forward grid (2 CTAs x 16 warps x SMs)
 
 __global__ void __launch_bounds__(256)
 bias_partial_kernel(int N, int K, const float* __restrict__ g0, float* __restrict__ bpart) {
@@ -1039,8 +1102,8 @@ add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ o
 }
 
 // -----------------------------------------------------------------------------
-// Fused interior step (stock Poisson residual): node packing for BOTH passes in one kernel, and the
-// residual epilogue that writes the backward's point-pair records directly (no gjets round trip).
+// Fused interior step (stock Poisson residual): node packing for BOTH passes in one kernel (the
+// residual epilogue itself runs inside the forward kernel: FwdEpilogue).
 // -----------------------------------------------------------------------------
 template <int KIND>
 __global__ void pack_nodes_step_kernel(int M, int Mfree, int npairs, int Mp,
@@ -1087,84 +1150,40 @@ __global__ void pack_nodes_step_kernel(int M, int Mfree, int npairs, int Mp,
   }
 }
 
-// res = scale (u_xx + u_yy + f),  f = amp sin(kx x) sin(ky y) + f0;  loss partial = sum res^2 / n_total;
-// dLoss/du_xx = dLoss/du_yy = g = 2 scale res / n_total  ->  the point-pair record of the backward:
-//   LAPL (Gaussian, g2_lapl_point):   {x,x',y,y'} {D,D',g4,g4'} {m,m',k3,k3'} {k4,k4',0,0}
-//   general layout (softplus-hat):    {x,x',y,y'} {0,0,0,0} {0,0,g,g'} {g,g',0,0}
-template <bool LAPL>
-__global__ void __launch_bounds__(256)
-poisson_residual_pack_kernel(int N, int N2, float inv_n, const float* __restrict__ x,
-                             const float* __restrict__ y, const float* __restrict__ jets, float scale,
-                             float amp, float kx, float ky, float f0, float4* __restrict__ recs,
-                             float* __restrict__ lpart) {
-  __shared__ float red[8];
-  const size_t n = (size_t)N;
-  float s = 0.f;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N2; p += gridDim.x * blockDim.x) {
-    const int i0 = 2 * p, i1 = 2 * p + 1;
-    const bool v1 = i1 < N;
-    // scalar loads: a warp still covers 256 contiguous bytes per array, and no alignment is assumed
-    const float xa = x[i0], ya = y[i0], la = jets[3 * n + i0] + jets[4 * n + i0];
-    const float xb = v1 ? x[i1] : xa, yb = v1 ? y[i1] : ya;
-    const float lb = v1 ? jets[3 * n + i1] + jets[4 * n + i1] : 0.f;
-    const float ra = scale * (la + fmaf(amp * sinf(kx * xa), sinf(ky * ya), f0));
-    const float rb = v1 ? scale * (lb + fmaf(amp * sinf(kx * xb), sinf(ky * yb), f0)) : 0.f;
-    s = fmaf(ra, ra, s);
-    s = fmaf(rb, rb, s);
-    const float ga = 2.f * scale * ra * inv_n, gb = 2.f * scale * rb * inv_n;
-    float4* r = recs + 4 * (size_t)p;
-    r[0] = make_float4(xa, xb, ya, yb);
-    if (LAPL) {
-      const G2LaplPoint ca = g2_lapl_point(ga, ga), cb = g2_lapl_point(gb, gb);
-      r[1] = make_float4(ca.D, cb.D, ca.g4, cb.g4);
-      r[2] = make_float4(ca.m, cb.m, ca.k3, cb.k3);
-      r[3] = make_float4(ca.k4, cb.k4, 0.f, 0.f);
-    } else {
-      r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      r[2] = make_float4(0.f, 0.f, ga, gb);
-      r[3] = make_float4(ga, gb, 0.f, 0.f);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += red[w];
-    lpart[blockIdx.x] = v * inv_n;
-  }
-}
-
 // -----------------------------------------------------------------------------
 // fast forward launcher (one instantiation per kernel kind / tile shape)
 // -----------------------------------------------------------------------------
 struct FastFwdArgs {
   int N; const float* x; const float* y; const float4* recs; int npairs, tile_pairs;
   const float* bias; float* jets; int vec_ok; size_t smem; int sms, dev; cudaStream_t s;
+  const FwdEpilogue* epi;      // non-null: run the residual epilogue (level 2 only)
+  int* nwarps_out;             // EPI: number of loss partials written (= warps of the grid)
 };
 
-template <int KIND, int P, int T, int B, int U, bool MIXED>
-static int launch_fast_fwd_m(const FastFwdArgs& a) {
+template <int KIND, int P, int T, int B, int U, bool MIXED, bool EPI>
+static int launch_fast_fwd_e(const FastFwdArgs& a) {
   const long long nwt = ((long long)a.N + 32 * P - 1) / (32 * P);
   long long blocks = (nwt + (T / 32) - 1) / (T / 32);
   if (blocks > (long long)a.sms * B) blocks = (long long)a.sms * B;
+  const FwdEpilogue ep = EPI ? *a.epi : FwdEpilogue{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr, nullptr};
+  if (EPI && a.nwarps_out) *a.nwarps_out = (int)blocks * (T / 32);
   static OnceFlags once;
   if (KIND == GAUSSIAN) {
-    auto kfn = g2k1_fwd_kernel<P, MIXED, T, B, U>;
+    auto kfn = g2k1_fwd_kernel<P, MIXED, T, B, U, EPI>;
     CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
-    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok);
+    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok, ep);
   } else {
-    auto kfn = s2k1_fwd_kernel<P, MIXED, T, B, U>;
+    auto kfn = s2k1_fwd_kernel<P, MIXED, T, B, U, EPI>;
     CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
-    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok);
+    kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok, ep);
   }
   LAUNCH_CHECK(KIND == GAUSSIAN ? "g2k1_fwd_kernel" : "s2k1_fwd_kernel");
   return SPINN_OK;
 }
 template <int KIND, int P, int T, int B, int U>
 static int launch_fast_fwd(bool mixed, const FastFwdArgs& a) {
-  return mixed ? launch_fast_fwd_m<KIND, P, T, B, U, true>(a) : launch_fast_fwd_m<KIND, P, T, B, U, false>(a);
+  if (a.epi) return launch_fast_fwd_e<KIND, P, T, B, U, false, true>(a);
+  return mixed ? launch_fast_fwd_e<KIND, P, T, B, U, true, false>(a) : launch_fast_fwd_e<KIND, P, T, B, U, false, false>(a);
 }
 
 // -----------------------------------------------------------------------------
@@ -1396,12 +1415,13 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
                          const float* x, const float* y, const float* xf, const float* yf,
                          const float* xfix, const float* yfix, const float* h, int hs,
                          const float* W, const float* bias, float* jets, void* ws, size_t ws_bytes,
-                         void* stream, bool nodes_packed = false) {
+                         void* stream, bool nodes_packed = false, const FwdEpilogue* epi = nullptr,
+                         int* nwarps_out = nullptr) {
   int rc = check_common(dim, kind, level, N, M_free, M_fixed, K);
   if (rc) return rc;
   if (N == 0) return SPINN_OK;
   const int M = M_free + M_fixed;
-  if (!x || (dim == 2 && !y) || !h || !W || !jets || (M_free && !xf) || (M_fixed && !xfix) ||
+  if (!x || (dim == 2 && !y) || !h || !W || (!jets && !epi) || (M_free && !xf) || (M_fixed && !xfix) ||
       (dim == 2 && ((M_free && !yf) || (M_fixed && !yfix))))
     return fail(SPINN_E_BADARG, "null pointer argument in jets_fwd");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1431,11 +1451,11 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
     const bool small = (long long)N < (long long)32 * 4 * 8 * sms;
     const int v = small ? 2 : tune.fwd;
     const bool sp = kind == SPINN_KIND_SOFTPLUS;
-    const FastFwdArgs fa = {N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok, smem, sms, cur_dev, s};
+    const FastFwdArgs fa = {N, x, y, recs, p.npairs, tile_pairs, bias, jets, vec_ok, smem, sms, cur_dev, s,
+                            epi, nwarps_out};
     int rcl;
     switch (v) {
       case 0: rcl = sp ? launch_fast_fwd<SOFTPLUS, 4, 256, 2, 1>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 4, 256, 2, 2>(mixed, fa); break;
-      case 1: rcl = sp ? launch_fast_fwd<SOFTPLUS, 2, 512, 2, 1>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 2, 512, 2, 2>(mixed, fa); break;
       case 2: rcl = sp ? launch_fast_fwd<SOFTPLUS, 1, 512, 2, 2>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 1, 512, 2, 4>(mixed, fa); break;
       default: rcl = sp ? launch_fast_fwd<SOFTPLUS, 2, 256, 2, 2>(mixed, fa) : launch_fast_fwd<GAUSSIAN, 2, 256, 2, 4>(mixed, fa); break;
     }
@@ -1695,7 +1715,7 @@ int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, i
   int rc = check_common(2, kind, 2, N, M_free, M_fixed, 1);
   if (rc) return rc;
   if (N <= 0 || n_total <= 0.0) return fail(SPINN_E_BADARG, "interior step needs N > 0 and n_total > 0");
-  if (!x || !y || !jets || !loss || !h || !W || !d_h || !d_W || (M_free && (!xc_free || !yc_free || !d_xc || !d_yc)) ||
+  if (!x || !y || !loss || !h || !W || !d_h || !d_W || (M_free && (!xc_free || !yc_free || !d_xc || !d_yc)) ||
       (M_fixed && (!xc_fixed || !yc_fixed)))
     return fail(SPINN_E_BADARG, "null pointer argument in poisson_interior_step");
   const int M = M_free + M_fixed;
@@ -1717,24 +1737,16 @@ int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, i
         M, M_free, fp.npairs, bp.Mp, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar, W, (float4*)ws_fwd,
         (float*)(bb + bp.off_soa));
   LAUNCH_CHECK("pack_nodes_step_kernel");
-  // 2. forward jets
+  // 2. forward jets + residual epilogue: loss partials (one per warp) and the backward's point-pair records
+  const FwdEpilogue ep = {scale, amp, kx, ky, f0, (float)(1.0 / n_total), (float4*)(bb + bp.off_pts),
+                          (float*)(bb + bp.off_loss)};
+  int nlp = 0;
   rc = jets_fwd_impl(2, kind, 2, N, M_free, M_fixed, 1, x, y, xc_free, yc_free, xc_fixed, yc_fixed, h, h_is_scalar,
-                     W, bias, jets, ws_fwd, ws_fwd_bytes, stream, true);
+                     W, bias, jets, ws_fwd, ws_fwd_bytes, stream, true, &ep, &nlp);
   if (rc) return rc;
-  // 3. residual, loss partials, point-pair records of the backward
-  const int N2 = (N + 1) / 2;
-  int blocks = ceil_div_i(N2, 256 * 2);
-  if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
-  const float inv_n = (float)(1.0 / n_total);
-  if (kind == SPINN_KIND_GAUSSIAN)
-    poisson_residual_pack_kernel<true><<<blocks, 256, 0, s>>>(N, N2, inv_n, x, y, jets, scale, amp, kx, ky, f0,
-                                                              (float4*)(bb + bp.off_pts), (float*)(bb + bp.off_loss));
-  else
-    poisson_residual_pack_kernel<false><<<blocks, 256, 0, s>>>(N, N2, inv_n, x, y, jets, scale, amp, kx, ky, f0,
-                                                               (float4*)(bb + bp.off_pts), (float*)(bb + bp.off_loss));
-  LAUNCH_CHECK("poisson_residual_pack_kernel");
-  // 4.-5. backward on the packed records + second stage (gradients, bias gradient = 0, loss)
-  const BwdFused fused = {blocks, loss};
+  if (nlp <= 0 || nlp > LOSS_BLOCKS) return fail(SPINN_E_CUDA, "unexpected forward grid (%d warps)", nlp);
+  // 3.-4. backward on the packed records + second stage (gradients, bias gradient = 0, loss)
+  const BwdFused fused = {nlp, loss};
   return jets_bwd_impl(2, kind, 2, 0x18, N, M_free, M_fixed, 1, x, y, xc_free, yc_free, xc_fixed, yc_fixed, h,
                        h_is_scalar, W, nullptr, d_xc, d_yc, d_h, d_W, d_bias, ws_bwd, ws_bwd_bytes, stream, &fused);
 }

@@ -21,10 +21,11 @@ UNIT_SOURCE = dict(scale=1.0, amp=0.0, kx=0.0, ky=0.0, f0=1.0)
 
 class PoissonInteriorStep:
     #: kernels of ours enqueued by one run() through spinn2d_poisson_interior_step: pack_nodes_step,
-    #: forward, residual epilogue (writes the backward's point records), backward, second stage.
+    #: forward (with the residual epilogue: loss partials + the backward's point records), backward,
+    #: second stage.
     #: structured=False / cutoff take the separate calls: pack_nodes(fwd), fwd, residual,
     #: add_partials, pack_nodes(bwd), pack_points, bwd, bias_partial, finalize
-    LAUNCHES = 5
+    LAUNCHES = 4
     LAUNCHES_SEPARATE = 9
 
     def __init__(self, nn, x, y, n_total=None, residual=SINE, structured=True, cutoff=None):
