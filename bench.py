@@ -36,10 +36,54 @@ UNIT = "point-node evals/s"
 # (13 recompute + 40) = 76.  The benchmarked Poisson residual only has u_xx,u_yy upstream
 # gradients, so its backward runs the structured variant: 8 (geometry) + 17 = 25 flops in 16
 # instructions (spinn_math.cuh:g2_bwd_pair_lapl) -> 48 per pair.
-FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 25.0
-MUFU_PER_PAIR = 2.0
-SMS, LANES, NOMINAL_MHZ = 148, 128, 1965.0
-NCU_DRAM_BYTES_BWD_STRUCTURED = 134.686976e6 + 6.896640e6      # profiles/r01f_ncu_full.txt
+SMS, LANES, MUFU_LANES, NOMINAL_MHZ = 148, 128, 16, 1965.0
+# Executed work per point-node pair of each kernel, counted in the SASS of the inner loops
+# (tools/sass_census.py -> profiles/r02_sass_inner_loops.txt): flop (FMA = 2), FP32-pipe instruction
+# slots (a packed FFMA2/FMUL2/FADD2 = one slot per lane-pair = 1 per pair), MUFU operations.
+KERNEL_COST = {
+    ("gaussian", "fwd"): dict(flop=23.0, instr=14, mufu=1),
+    ("gaussian", "bwd_structured"): dict(flop=25.0, instr=16, mufu=1),
+    ("gaussian", "bwd_general"): dict(flop=53.0, instr=32, mufu=1),
+    ("softplus", "fwd"): dict(flop=42.0, instr=30, mufu=5),
+    ("softplus", "bwd_structured"): dict(flop=74.0, instr=51, mufu=4),
+    ("softplus", "bwd_general"): dict(flop=95.0, instr=63, mufu=5),
+}
+FLOP_FWD, FLOP_BWD_GENERAL, FLOP_BWD_STRUCTURED = 23.0, 53.0, 25.0      # Gaussian (23 + 53 = 76)
+NCU_KERNELS_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_kernels.json")
+
+
+def kernel_report(kind, which, pairs, ms, clk_mhz):
+    """Achieved rates of one kernel launch against the nominal pipes at the SM clock sampled during
+    the timed region: FP32 148 SM x 128 lanes x 2 flop, MUFU 148 SM x 16 lanes."""
+    c = KERNEL_COST[(kind, which)]
+    t = ms * 1e-3
+    fp32_peak = SMS * LANES * 2 * clk_mhz * 1e6
+    lane_rate = SMS * LANES * clk_mhz * 1e6
+    mufu_rate = SMS * MUFU_LANES * clk_mhz * 1e6
+    slots = pairs * c["instr"] / t / lane_rate
+    mufu = pairs * c["mufu"] / t / mufu_rate
+    return {"ms": ms, "pairs_per_s": pairs / t, "tflops": pairs * c["flop"] / t / 1e12,
+            "frac": pairs * c["flop"] / t / fp32_peak, "flop_per_pair": c["flop"],
+            "fp32_instr_per_pair": c["instr"], "fp32_slot_frac": slots,
+            "mufu_per_pair": c["mufu"], "mufu_frac": mufu,
+            "binding_pipe": "mufu" if mufu > slots else "fp32", "binding_pipe_frac": max(mufu, slots)}
+
+
+def ncu_traffic(kernel_prefix, N, M):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture of this workload (tools/ncu_summary.py json); None if the file
+    does not cover it."""
+    try:
+        d = json.load(open(NCU_KERNELS_JSON))
+        if d.get("points") != N or d.get("nodes") != M:
+            return None
+        for name, k in d["kernels"].items():
+            if name.startswith(kernel_prefix):
+                return {"bytes": k["dram_bytes_read"] + k["dram_bytes_write"], "kernel": name,
+                        "source": os.path.relpath(NCU_KERNELS_JSON, os.path.dirname(NCU_KERNELS_JSON) + "/..")}
+    except Exception:
+        pass
+    return None
 
 
 def workload_name(kind, n_points, n_nodes):
@@ -60,6 +104,7 @@ def parse():
     p.add_argument("--cpu-chunk", type=int, default=16384)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-softplus", action="store_true", help="skip the softplus-hat leg of the default line")
     p.add_argument("--general-backward", action="store_true",
                    help="time the general 5-row backward instead of the structured (u_xx,u_yy) one")
     return p.parse_args()
@@ -303,8 +348,6 @@ def run_ours(args):
     del xs_all, ys_all
     n_loc = hi - lo
     step = PoissonInteriorStep(nn, xs, ys, n_total=N, structured=not args.general_backward)
-    FLOP_BWD = FLOP_BWD_GENERAL if args.general_backward else FLOP_BWD_STRUCTURED
-    FLOP_PER_PAIR = FLOP_FWD + FLOP_BWD
 
     def barrier():
         if ws > 1:
@@ -578,54 +621,99 @@ def run_ours(args):
 
     peaks = microbench_peaks(lib, dev)
     clocks = clk.summary()
-    nominal_fp32 = SMS * LANES * 2 * NOMINAL_MHZ * 1e6          # flop/s
-    measured_fp32 = 2.0 * max(peaks["ffma_3reg"], peaks["ffma_shared"], peaks["ffma2_shared"])  # flop/s
-    ach_bwd = pairs_loc * FLOP_BWD / (ms_bwd * 1e-3)
-    ach_fwd = pairs_loc * FLOP_FWD / (ms_fwd * 1e-3)
+    clk_mhz = clocks.get("sm_mhz") or NOMINAL_MHZ
+    kind = args.kind
+    bwd_which = "bwd_general" if args.general_backward else "bwd_structured"
+    k_fwd = kernel_report(kind, "fwd", pairs_loc, ms_fwd, clk_mhz)
+    k_bwd = kernel_report(kind, bwd_which, pairs_loc, ms_bwd, clk_mhz)
+    FLOP_PER_PAIR = k_fwd["flop_per_pair"] + k_bwd["flop_per_pair"]
+    fp32_peak = SMS * LANES * 2 * clk_mhz * 1e6                 # flop/s at the clock seen under load
     ach_step = N * M * FLOP_PER_PAIR / (ms_step * 1e-3) / ws
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-    hbm_bytes_step = 60.0 * n_loc + 64.0 * n_loc / 2 * 2          # jets/gjets/x/y + packed point records w+r
+    # per step and point: x,y read twice (8+8 B), jets written (20 B), point-pair records written by the
+    # forward epilogue and read by the backward (32 B each way)
+    hbm_bytes_step = (16.0 + 20.0 + 64.0) * n_loc
+    dom_prefix = ("g2k1_bwd_kernel" if kind == "gaussian" else "s2k1_bwd_kernel")
+    traffic = ncu_traffic(dom_prefix, N, M) if (ws == 1 and not args.general_backward) else None
+    probe_fp32 = 2.0 * max(peaks["ffma_3reg"], peaks["ffma_shared"], peaks["ffma2_shared"])
     roofline = {
-        "bound": "fp32", "kernel": "g2k1_bwd_kernel (%s upstream)" % ("general 5-row" if args.general_backward else "structured u_xx,u_yy"),
-        "achieved": ach_bwd / 1e12, "peak": measured_fp32 / 1e12, "unit": "TFLOP/s",
-        "frac": ach_bwd / measured_fp32,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
-        # `ncu --set full` capture (profiles/r01f_ncu_full.txt), valid for the default workload only
-        "traffic": (NCU_DRAM_BYTES_BWD_STRUCTURED if (N == 4194304 and M == 4096 and ws == 1
-                                                      and not args.general_backward) else None),
+        "bound": "fp32", "kernel": "%s (%s upstream)" % (dom_prefix, "general 5-row" if args.general_backward
+                                                          else "structured u_xx,u_yy"),
+        "achieved": k_bwd["tflops"], "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": k_bwd["frac"],
+        "peak_source": "nominal FP32 rate 148 SM x 128 lanes x 2 flop x %.0f MHz (SM clock sampled during the timed "
+                       "region); MEASURED_PEAKS.json holds no FP32/MUFU figure.  The in-run FMA probe "
+                       "(register-only FFMA chains, 64 warps/SM) is listed under `probe`." % clk_mhz,
+        "probe": {"fp32_tflops": probe_fp32 / 1e12, "frac_of_probe": k_bwd["tflops"] * 1e12 / probe_fp32,
+                  "mufu_ex2_gops": peaks["ex2"] / 1e9},
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
+        # capture of this very workload (profiles/r02_ncu_kernels.json, regenerated by tools/ncu_summary.py)
+        "traffic": traffic["bytes"] if traffic else None,
+        "traffic_source": traffic,
         # point-pair records (4 x 16 B) read once + per-chunk partial sums (4 rows x M floats) written;
         # chunks = 2 waves x SMs x 2 CTAs/SM / node groups of 1024
         "traffic_algorithmic": (64.0 * (n_loc / 2) + 16.0 * M * (2 * SMS * 2 // max(1, -(-M // 1024)))
                                 if not args.general_backward else None),
-        "peak_source": "best in-run FMA probe (spinn_microbench: FFMA/FFMA2 chains, register operands, 64 warps/SM), lane-FMA/s x 2",
-        "peak_nominal": nominal_fp32 / 1e12, "frac_of_nominal": ach_bwd / nominal_fp32,
-        "algorithmic_flop_per_pair": {"fwd": FLOP_FWD, "bwd": FLOP_BWD, "step": FLOP_PER_PAIR,
-                                      "bwd_general_5_rows": FLOP_BWD_GENERAL},
+        "algorithmic_flop_per_pair": {"fwd": k_fwd["flop_per_pair"], "bwd": k_bwd["flop_per_pair"],
+                                      "step": FLOP_PER_PAIR, "survey_8d_general_gaussian": 76.0},
         "kernels": {
-            "fwd": {"ms": ms_fwd, "tflops": ach_fwd / 1e12, "frac": ach_fwd / measured_fp32},
-            "bwd": {"ms": ms_bwd, "tflops": ach_bwd / 1e12, "frac": ach_bwd / measured_fp32},
-            "step": {"ms": ms_step, "tflops_per_gpu": ach_step / 1e12, "frac": ach_step / measured_fp32,
-                     "frac_of_nominal": ach_step / nominal_fp32},
+            "fwd": k_fwd, "bwd": k_bwd,
+            "step": {"ms": ms_step, "tflops_per_gpu": ach_step / 1e12, "frac": ach_step / fp32_peak},
         },
-        "mufu": {"achieved_gops": pairs_loc * MUFU_PER_PAIR / ((ms_fwd + ms_bwd) * 1e-3) / 1e9,
-                 "peak_gops": peaks["ex2"] / 1e9,
-                 "frac": pairs_loc * MUFU_PER_PAIR / ((ms_fwd + ms_bwd) * 1e-3) / peaks["ex2"]},
+        "mufu": {"achieved_gops": pairs_loc * (k_fwd["mufu_per_pair"] + k_bwd["mufu_per_pair"])
+                 / ((ms_fwd + ms_bwd) * 1e-3) / 1e9,
+                 "peak_gops": SMS * MUFU_LANES * clk_mhz * 1e-3,
+                 "frac": pairs_loc * (k_fwd["mufu_per_pair"] + k_bwd["mufu_per_pair"])
+                 / ((ms_fwd + ms_bwd) * 1e-3) / (SMS * MUFU_LANES * clk_mhz * 1e6)},
         "hbm": {"achieved_gbs": hbm_bytes_step / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": hbm_bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
         "microbench_lane_ops_per_s": peaks,
-        # FP32-pipe instruction slots: per pair the kernels issue 14 (fwd) / 16 (structured bwd) /
-        # 32 (general bwd) FP32 instructions; lanes x clock = 148 SM x 128 x 1.965 GHz.  (flop-based
-        # `frac` is lower because adds/multiplies count 1 flop and FMAs 2 for the same slot.)
-        "fp32_issue_slots": {
-            "instr_per_pair": {"fwd": 14, "bwd": 32 if args.general_backward else 16},
-            "fwd_frac_of_lane_rate": pairs_loc * 14 / (ms_fwd * 1e-3) / (nominal_fp32 / 2),
-            "bwd_frac_of_lane_rate": pairs_loc * (32 if args.general_backward else 16) / (ms_bwd * 1e-3) / (nominal_fp32 / 2),
-            "probe_same_mix_frac": "0.775 (16 warps/SM) .. 0.824 (64 warps/SM), profiles/r01_microbench_probes.txt"},
+        "notes": "fp32_slot_frac = FP32-pipe instruction slots issued / (148 SM x 128 lanes x clock): packed "
+                 "FMUL2/FADD2 cost the pipe as much as FFMA2 (profiles/r02a_microbench_probes.txt, probes "
+                 "15-18: 92-95 % of the lane rate each), so the flop-based `frac` understates pipe occupancy "
+                 "by the add/mul share of the mix; a register-only probe of the forward's own mix reaches "
+                 "0.776 (probe 19).",
     }
+
+    # the softplus-hat kernel on the same point set: same fused step, MUFU-bound forward
+    softplus = None
+    if ws == 1 and kind == "gaussian" and not args.general_backward and not args.no_softplus:
+        try:
+            pde_s, nn_s = synthetic.make_state(args.nodes, args.b_nodes, args.samples, "softplus", device=dev)
+            sstep = PoissonInteriorStep(nn_s, xs, ys, n_total=N)
+            for _ in range(2):
+                sstep.run(all_reduce=False)
+            ms_s = time_call(lambda: sstep.run(all_reduce=False), reps=3)
+            sstep.run(all_reduce=False, separate=True)
+            ls1, ls2 = nn_s.layer1, nn_s.layer2
+
+            def s_fwd():
+                assert lib.spinn2d_jets_fwd(1, 2, n_loc, sstep.Mf, sstep.Mx, 1, P(xs), P(ys), P(ls1.x), P(ls1.y),
+                                            P(ls1.xf), P(ls1.yf), P(ls1.h), 0, P(ls2.weight), P(ls2.bias),
+                                            P(sstep.jets), P(sstep.ws_f), sstep.ws_f.numel(), S()) == 0
+
+            def s_bwd():
+                q = sstep.pack
+                assert lib.spinn2d_jets_bwd(1, 2, 0x18, n_loc, sstep.Mf, sstep.Mx, 1, P(xs), P(ys), P(ls1.x),
+                                            P(ls1.y), P(ls1.xf), P(ls1.yf), P(ls1.h), 0, P(ls2.weight),
+                                            P(sstep.gjets), P(q.view("d_x")), P(q.view("d_y")), P(q.view("d_h")),
+                                            P(q.view("d_W")), P(q.view("d_b")), P(sstep.ws_b), sstep.ws_b.numel(),
+                                            S()) == 0
+
+            sf = kernel_report("softplus", "fwd", pairs_loc, time_call(s_fwd, reps=3), clk_mhz)
+            sb = kernel_report("softplus", "bwd_structured", pairs_loc, time_call(s_bwd, reps=3), clk_mhz)
+            softplus = {"value": N * M / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
+                        "loss": float(sstep.pack.view("loss")[0]), "kernels": {"fwd": sf, "bwd": sb},
+                        "what": "the same fused interior step with the softplus-hat kernel (spinn2d.py:195-205): "
+                                "s2k1_fwd_kernel is MUFU-bound (5 MUFU + 30 FP32 slots per pair), s2k1_bwd_kernel "
+                                "FP32-bound (51 slots + 4 MUFU); reference CPU rate for this kernel: 4.4e6 evals/s "
+                                "on 8 threads (BASELINE.md section 2)"}
+            del sstep, pde_s, nn_s
+        except Exception as exc:  # pragma: no cover
+            softplus = {"error": repr(exc)[:300]}
 
     # the general 5-row backward on the same inputs (what a residual using all jets would cost)
     general = None
@@ -645,7 +733,8 @@ def run_ours(args):
         nloss = step.pack.slices["loss"][0]
         diff = float((gstep.pack.flat[:nloss] - step.pack.flat[:nloss]).abs().max()
                      / step.pack.flat[:nloss].abs().max())
-        general = {"bwd_ms": ms_g, "bwd_tflops": pairs_loc * FLOP_BWD_GENERAL / (ms_g * 1e-3) / 1e12,
+        general = {"bwd_ms": ms_g, "bwd_tflops": pairs_loc * KERNEL_COST[(kind, "bwd_general")]["flop"] / (ms_g * 1e-3) / 1e12,
+                   "kernel": kernel_report(kind, "bwd_general", pairs_loc, ms_g, clk_mhz),
                    "step_ms_equivalent": ms_step - ms_bwd + ms_g,
                    "evals_per_s_equivalent": N * M / ((ms_step - ms_bwd + ms_g) * 1e-3),
                    "max_rel_diff_vs_structured": diff,
@@ -734,7 +823,7 @@ def run_ours(args):
         "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
         "clocks": clocks, "e2e": e2e, "gpu_launches": (PoissonInteriorStep.LAUNCHES_SEPARATE if args.general_backward
                                                         else PoissonInteriorStep.LAUNCHES) * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "general_upstream": general,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "general_upstream": general, "softplus": softplus,
         "compact_support_opt_in": compact,
         "reference_algorithm_on_this_gpu": gpu_eager,
     }

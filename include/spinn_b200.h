@@ -121,7 +121,7 @@ size_t spinn2d_poisson_residual_workspace_bytes(int N);
  * Four launches: node constants of both passes; forward jets WITH the residual epilogue (loss
  * partials and the backward's point-pair records are written by the forward kernel itself -- the
  * upstream gradient never exists as an [5][N] array); structured backward; second stage
- * (gradients + loss).  jets [5][N] (may be NULL: not stored) and *loss are overwritten;
+ * (gradients + loss).  jets [5][N] and *loss are overwritten;
  * gradients as in spinn2d_jets_bwd (d_bias, if given, receives 0: the residual does not depend on u).
  * ws_fwd / ws_bwd: sized by spinn2d_fwd_workspace_bytes / spinn2d_bwd_workspace_bytes. */
 int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, int M_fixed,

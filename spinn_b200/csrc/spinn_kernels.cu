@@ -387,15 +387,58 @@ __device__ __forceinline__ void write_point_record(float4* __restrict__ r, float
   }
 }
 
+// The epilogue of one warp-tile, fed from global memory (the thread re-reads the u_xx, u_yy it has
+// stored itself: L2 hits).  It runs in a second walk over the warp's tiles AFTER the jets loop:
+// placed inside that loop it changed nothing in the inner loop's instruction count but perturbed
+// ptxas' schedule of it enough to cost 4 % of the kernel (profiles/r02c: 8.08 vs 7.76 ms).
+// Returns this thread's sum of res^2.
+template <int KIND, int P>
+__device__ __forceinline__ float fwd_epilogue_tile(long long i0, int lim, int N, const float* __restrict__ x,
+                                                const float* __restrict__ y, const float* jets,
+                                                const FwdEpilogue& ep) {
+  const int lane = threadIdx.x & 31;
+  float px[P], py[P], g[P], s = 0.f;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const bool v = i0 + q < lim;
+    px[q] = v ? x[i0 + q] : 0.f;
+    py[q] = v ? y[i0 + q] : 0.f;
+    const float lap = v ? jets[3 * (size_t)N + i0 + q] + jets[4 * (size_t)N + i0 + q] : 0.f;
+    const float res = v ? ep.scale * (lap + fmaf(ep.amp * sinf(ep.kx * px[q]), sinf(ep.ky * py[q]), ep.f0)) : 0.f;
+    s = fmaf(res, res, s);
+    g[q] = 2.f * ep.scale * res * ep.inv_n;
+  }
+  if (P == 1) {
+    // one point per thread: lanes (2k, 2k+1) form the pair (tile bases are multiples of 32)
+    const float xb = __shfl_down_sync(0xffffffffu, px[0], 1), yb = __shfl_down_sync(0xffffffffu, py[0], 1);
+    const float gb = __shfl_down_sync(0xffffffffu, g[0], 1);
+    if ((lane & 1) == 0 && i0 < lim) {
+      const bool v1 = i0 + 1 < lim;
+      write_point_record<KIND>(ep.recs + 4 * (size_t)(i0 >> 1), px[0], v1 ? xb : px[0], py[0], v1 ? yb : py[0],
+                               g[0], v1 ? gb : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < P; q += 2) {
+      if (i0 + q < lim) {
+        const bool v1 = i0 + q + 1 < lim;
+        write_point_record<KIND>(ep.recs + 4 * (size_t)((i0 + q) >> 1), px[q], v1 ? px[(q + 1) % P] : px[q], py[q],
+                                 v1 ? py[(q + 1) % P] : py[q], g[q], v1 ? g[(q + 1) % P] : 0.f);
+      }
+    }
+  }
+  return s;
+}
+
 // One span of the point set, walked in warp-tiles of 32*P consecutive points: tile `wt` of the span
 // starts at point `base + wt*32*P`; the span ends at `end`.  COOP: all warps of the CTA run the same
 // number of iterations (the multi-tile node loop has block-wide barriers).
-template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP, bool EPI>
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP>
 __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N, const float* __restrict__ x,
                                             const float* __restrict__ y, const float4* __restrict__ recs,
                                             const float4* __restrict__ sm4w, float4* __restrict__ sm4, int npairs,
                                             int tile_pairs, float b0, float* __restrict__ jets, bool vec,
-                                            long long gw, long long nwarps, const FwdEpilogue& ep, float& lsum) {
+                                            long long gw, long long nwarps) {
   constexpr int NJ = MIXED ? 6 : 5;
   const int lane = threadIdx.x & 31;
   const long long nwt = (end - base + 32 * P - 1) / (32 * P);
@@ -435,40 +478,25 @@ __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N
 #pragma unroll
         for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
         // `lim` (not N) bounds the stores of this span; the jets rows are N long
-        if (!EPI || jets != nullptr) store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
-      }
-    }
-    if (EPI && active) {
-      float g[P];
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        const bool v = i0 + q < lim;
-        const float lap = (acc[q][3].x + acc[q][3].y) + (acc[q][4].x + acc[q][4].y);
-        const float res = v ? ep.scale * (lap + fmaf(ep.amp * sinf(ep.kx * px[q]), sinf(ep.ky * py[q]), ep.f0)) : 0.f;
-        lsum = fmaf(res, res, lsum);
-        g[q] = 2.f * ep.scale * res * ep.inv_n;
-      }
-      if (P == 1) {
-        // one point per thread: lanes (2k, 2k+1) form the pair (tile bases are multiples of 32)
-        const float xb = __shfl_down_sync(0xffffffffu, px[0], 1), yb = __shfl_down_sync(0xffffffffu, py[0], 1);
-        const float gb = __shfl_down_sync(0xffffffffu, g[0], 1);
-        if ((lane & 1) == 0 && i0 < lim) {
-          const bool v1 = i0 + 1 < lim;
-          write_point_record<KIND>(ep.recs + 4 * (size_t)(i0 >> 1), px[0], v1 ? xb : px[0], py[0], v1 ? yb : py[0],
-                                   g[0], v1 ? gb : 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < P; q += 2) {
-          if (i0 + q < lim) {
-            const bool v1 = i0 + q + 1 < lim;
-            write_point_record<KIND>(ep.recs + 4 * (size_t)((i0 + q) >> 1), px[q], v1 ? px[(q + 1) % P] : px[q], py[q],
-                                     v1 ? py[(q + 1) % P] : py[q], g[q], v1 ? g[(q + 1) % P] : 0.f);
-          }
-        }
+        store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
       }
     }
   }
+}
+
+// Second walk over the same warp-tiles, after the jets of ALL of this warp's tiles are stored: the
+// residual epilogue (kept out of the jets loop so that the hot loop's code is the plain kernel's).
+template <int KIND, int P>
+__device__ __forceinline__ float k1_fwd_epilogue_span(long long base, long long end, int N,
+                                                      const float* __restrict__ x, const float* __restrict__ y,
+                                                      const float* jets, long long gw, long long nwarps,
+                                                      const FwdEpilogue& ep) {
+  const int lane = threadIdx.x & 31;
+  const long long nwt = (end - base + 32 * P - 1) / (32 * P);
+  float s = 0.f;
+  for (long long wt = gw; wt < nwt; wt += nwarps)
+    s += fwd_epilogue_tile<KIND, P>(base + (wt * 32 + lane) * P, (int)end, N, x, y, jets, ep);
+  return s;
 }
 
 // Persistent CTAs.  Main span: as many FULL rounds (every warp one tile of 32*P points) as fit;
@@ -509,14 +537,19 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
     mbar_wait(&bar, 0);
     const long long round_pts = nwarps * 32 * P;
     const long long main_end = P == 1 ? (long long)N : ((long long)N / round_pts) * round_pts;
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false, EPI>(0, main_end, N, x, y, recs, sm4, sm4, npairs,
-                                                             tile_pairs, b0, jets, vec, gw, nwarps, ep, lsum);
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false>(0, main_end, N, x, y, recs, sm4, sm4, npairs, tile_pairs,
+                                                        b0, jets, vec, gw, nwarps);
     if (P > 1 && main_end < N)
-      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false, EPI>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
-                                                               tile_pairs, b0, jets, vec, gw, nwarps, ep, lsum);
+      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
+                                                          tile_pairs, b0, jets, vec, gw, nwarps);
+    if (EPI) {
+      lsum = k1_fwd_epilogue_span<KIND, P>(0, main_end, N, x, y, jets, gw, nwarps, ep);
+      if (P > 1 && main_end < N) lsum += k1_fwd_epilogue_span<KIND, 1>(main_end, N, N, x, y, jets, gw, nwarps, ep);
+    }
   } else {
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true, EPI>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
-                                                            jets, vec, gw, nwarps, ep, lsum);
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
+                                                       jets, vec, gw, nwarps);
+    if (EPI) lsum = k1_fwd_epilogue_span<KIND, P>(0, N, N, x, y, jets, gw, nwarps, ep);
   }
   if (EPI) {                                       // one loss partial per warp, every warp writes its slot
 #pragma unroll
@@ -1421,7 +1454,7 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
   if (rc) return rc;
   if (N == 0) return SPINN_OK;
   const int M = M_free + M_fixed;
-  if (!x || (dim == 2 && !y) || !h || !W || (!jets && !epi) || (M_free && !xf) || (M_fixed && !xfix) ||
+  if (!x || (dim == 2 && !y) || !h || !W || !jets || (M_free && !xf) || (M_fixed && !xfix) ||
       (dim == 2 && ((M_free && !yf) || (M_fixed && !yfix))))
     return fail(SPINN_E_BADARG, "null pointer argument in jets_fwd");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1715,7 +1748,7 @@ int spinn2d_poisson_interior_step(int kind, int N, double n_total, int M_free, i
   int rc = check_common(2, kind, 2, N, M_free, M_fixed, 1);
   if (rc) return rc;
   if (N <= 0 || n_total <= 0.0) return fail(SPINN_E_BADARG, "interior step needs N > 0 and n_total > 0");
-  if (!x || !y || !loss || !h || !W || !d_h || !d_W || (M_free && (!xc_free || !yc_free || !d_xc || !d_yc)) ||
+  if (!x || !y || !jets || !loss || !h || !W || !d_h || !d_W || (M_free && (!xc_free || !yc_free || !d_xc || !d_yc)) ||
       (M_fixed && (!xc_fixed || !yc_fixed)))
     return fail(SPINN_E_BADARG, "null pointer argument in poisson_interior_step");
   const int M = M_free + M_fixed;

@@ -8,6 +8,8 @@ against the fp64 oracle; bar 2e-5 (the reference's OWN fp32 path sits at 0.5-1.5
 same cases, see test_oracle_golden.py::test_reference_fp32_noise_floor_documented), and
 in addition new-vs-fp64 must stay within 3x of reference-fp32-vs-fp64 (+5e-6).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -344,6 +346,85 @@ def test_beyond_baseline_size_16m_points_16384_nodes():
     assert torch.equal(flat, step.run(all_reduce=False))
 
 
+def reference_fp32_error(dim, kind, x, y, xf, yf, xfix, yfix, h, W, b, g_masked, oracle_jets, oracle_grads):
+    """How far the REFERENCE's fp32 arithmetic (dense (N,M) tensors + nested autograd.grad: oracle/
+    torch_port.py, pinned against reference-generated fixtures to <= 5e-6) is from the fp64 oracle on
+    the same inputs, per quantity, in the mixed metric.  The earned slack of a parity bar."""
+    from oracle import torch_port as tp
+    nj = g_masked.shape[0]
+    full = 6 if dim == 2 else 3
+    g = np.zeros((full,) + g_masked.shape[1:], np.float32)
+    g[:nj] = g_masked
+    if dim == 2:
+        out = tp.jets_and_grads2d(kind, x, y, xf, yf, xfix, yfix, h, W, b, g)
+    else:
+        out = tp.jets_and_grads1d(kind, x, xf, xfix, h, W, b, g)
+    err = {"jets": [mixed_err(out["jets"][a], oracle_jets[a]) for a in range(nj)]}
+    for key in ("d_xc", "d_yc", "d_h", "d_W", "d_b"):
+        if key in out and out[key] is not None and np.size(out[key]):
+            err[key] = mixed_err(np.asarray(out[key]).reshape(np.asarray(oracle_grads[key]).shape), oracle_grads[key])
+    return err
+
+
+def bar(kind, ref_err):
+    """2e-5, or twice the reference's own fp32 error on the same inputs where that is larger."""
+    return max(TOL, 2.0 * ref_err)
+
+
+def load_dense(kind):
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"dense_{kind}.npz"))
+    return {k: (d[k].item() if d[k].ndim == 0 else d[k]) for k in d.files}
+
+
+@pytest.mark.parametrize("copies", [1, 96])
+@pytest.mark.parametrize("kind", ["gaussian", "softplus"])
+def test_baseline_density_vs_reference_generated_values(kind, copies):
+    """BASELINE density (h = 1/64, the 4096-node synthetic state): jets and parameter gradients at
+    2048 points of the collocation grid against values produced BY THE REFERENCE in fp32 and fp64
+    (tests/golden/dense_*.npz).  copies = 96 tiles the point set to 196 608 points so that the
+    two-points-per-thread main span of the persistent forward (and its one-point tail) is what
+    runs; upstream gradients are divided by the number of copies (gradients are sums over points)."""
+    c = load_dense(kind)
+    be = backend()
+    rep = lambda a: np.tile(a, copies)
+    x, y = rep(c["x"]), rep(c["y"])
+    n0 = c["x"].size
+    args = (T(x), T(y), T(c["xf"]), T(c["yf"]), T(c["xfix"]), T(c["yfix"]), T(c["h"]), T(c["W"]))
+    report = {}
+    for level in (2, 3):
+        jets = be.forward(2, cf.kind_id(kind), level, *args, T(c["b"])).cpu().numpy()[:, :, 0]
+        for a in range(5):
+            got = jets[a].reshape(copies, n0)
+            assert np.array_equal(got, np.broadcast_to(got[0], got.shape)), (level, a)       # every copy identical
+            e64 = mixed_err(got[0], c["jets_f64"][a])
+            e32 = mixed_err(got[0], c["jets_f32"][a])
+            eref = mixed_err(c["jets_f32"][a], c["jets_f64"][a])
+            report[f"jet{a}_L{level}"] = (e64, e32, eref)
+            assert e64 < TOL, (kind, level, a, e64)
+            assert e64 < 1.5 * eref + 3e-6 and e32 < 3e-5, (kind, level, a, e64, e32, eref)
+    for suffix, g, mask in (("", c["gjets"], 0), ("_lapl", c["gjets_lapl"], 0x18)):
+        gd = np.tile(g / copies, (1, copies)).astype(np.float32)
+        if mask:
+            gd[:3] = np.nan                                   # absent rows are never read
+        grads = be.backward(2, cf.kind_id(kind), 2, *args, T(gd[:, :, None]), True, mask)
+        for got, key in zip(grads, ("d_xc", "d_yc", "d_h", "d_W", "d_b")):
+            got = got.cpu().numpy().reshape(-1)
+            r64, r32 = c[key + suffix + "_f64"].reshape(-1), c[key + suffix + "_f32"].reshape(-1)
+            e64, e32, eref = mixed_err(got, r64), mixed_err(got, r32), mixed_err(r32, r64)
+            report[key + suffix] = (e64, e32, eref)
+            assert e64 < TOL, (kind, key + suffix, e64)
+            assert e64 < 1.5 * eref + 3e-6 and e32 < 3e-5, (kind, key + suffix, e64, e32, eref)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        import json
+        with open(os.path.join(out_dir, f"parity_dense_{kind}_x{copies}.json"), "w") as f:
+            json.dump({k: {"ours_vs_ref_fp64": v[0], "ours_vs_ref_fp32": v[1], "ref_fp32_vs_ref_fp64": v[2]}
+                       for k, v in report.items()}, f, indent=1)
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("mask", [0x18, 0x08, 0x10, 0x01, 0x19, 0x06, 0x0C, 0x0F, 0x1F])
 @pytest.mark.parametrize("kind,K", [("gaussian", 1), ("gaussian", 3), ("softplus", 1)])
 def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
@@ -363,11 +444,16 @@ def test_present_mask_rows_are_zero_and_never_read(mask, kind, K):
     xc = np.concatenate([c["xf"], c["xfix"]])
     yc = np.concatenate([c["yf"], c["yfix"]])
     G = cf.grads2d(kind, c["x"], c["y"], xc, yc, c["h"], c["W"], g, n_free=len(c["xf"]))
+    # seeded random clouds (301+40 random centres, heavy cancellation in d_h): the slack over 2e-5 is
+    # whatever the reference's own fp32 arithmetic needs on these very inputs
+    J = cf.jets2d(kind, c["x"], c["y"], xc, yc, c["h"], c["W"], np.zeros(K))
+    ref = reference_fp32_error(2, kind, c["x"], c["y"], c["xf"], c["yf"], c["xfix"], c["yfix"], c["h"], c["W"],
+                               np.zeros(K, np.float32), g, J, G)
     for got, key in zip(grads, ("d_xc", "d_yc", "d_h", "d_W", "d_b")):
         got = got.cpu().numpy()
         assert np.all(np.isfinite(got)), (mask, key)
-        # seeded random clouds (301+40 random centres, heavy cancellation in d_h): 1.5x the golden-case bar
-        assert mixed_err(got, G[key]) < 1.5 * tol_for(kind), (mask, kind, K, key, mixed_err(got, G[key]))
+        e = mixed_err(got, G[key])
+        assert e < bar(kind, ref.get(key, 0.0)), (mask, kind, K, key, e, ref.get(key))
 
 
 def _sweep_cases():
@@ -421,14 +507,17 @@ def test_random_shape_sweep(i, dim, kind, K, N, Mf, Mx, level):
         keys = ("d_xc", None, "d_h", "d_W", "d_b")
     jets = be.forward(dim, kid, level, *args, T(b)).cpu().numpy()
     # a handful of wide, randomly placed nodes -> sums with heavy cancellation (|sum| << sum|terms|):
-    # fp32 round-off of any evaluation order, the reference's included, shows up as a few 1e-5 here
-    tol = 3.0 * tol_for(kind)
+    # fp32 round-off of any evaluation order shows up as a few 1e-5 here; the bar is 2e-5 or twice
+    # what the reference's own fp32 arithmetic is off on the same inputs
+    ref = reference_fp32_error(dim, kind, x, y, xf, yf, xx, yx, h, W, b, gm, J, G)
     for a in range(nj):
-        assert mixed_err(jets[a], J[a]) < tol, (a, mixed_err(jets[a], J[a]))
+        e = mixed_err(jets[a], J[a])
+        assert e < bar(kind, ref["jets"][a]), (a, e, ref["jets"][a])
     grads = be.backward(dim, kid, level, *args, T(g), True, mask)
     for got, key in zip(grads, keys):
         if key is None:
             continue
         got = got.cpu().numpy()
         assert got.shape == np.asarray(G[key]).shape
-        assert mixed_err(got, G[key]) < tol, (key, mixed_err(got, G[key]))
+        e = mixed_err(got, G[key])
+        assert e < bar(kind, ref.get(key, 0.0)), (key, e, ref.get(key))

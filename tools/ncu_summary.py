@@ -3,6 +3,10 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv  > profiles/rNN_launches.txt
     python tools/ncu_summary.py full gpurun_out/prof.ncu-rep      > profiles/rNN_ncu_full.txt
+    python tools/ncu_summary.py json "<workload>" a.ncu-rep [b.ncu-rep ...] > profiles/rNN_ncu_kernels.json
+
+The json form is what bench.py reads `roofline.traffic` from (dram__bytes_read.sum +
+dram__bytes_write.sum per launch of the dominant kernel): regenerate it after every capture.
 """
 import csv
 import subprocess
@@ -18,6 +22,7 @@ KEYS = [
     "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -72,5 +77,49 @@ def full(path):
                 print(f"  {k:85s} {r[idx[k]]:>18s} {units[idx[k]]}")
 
 
+def _num(v, unit):
+    x = float(v.replace(",", ""))
+    scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-3, "usecond": 1e-3, "ms": 1.0,
+             "msecond": 1.0, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}
+    return x * scale.get(unit, 1.0)
+
+
+def as_json(workload, paths):
+    import json
+    import re
+    m1, m2 = re.search(r"points=(\d+)", workload), re.search(r"nodes=(\d+)", workload)
+    out = {"workload": workload, "points": int(m1.group(1)) if m1 else None,
+           "nodes": int(m2.group(1)) if m2 else None, "source": paths, "how": "ncu --set full --clock-control none (one launch each; "
+           "averaged over the launches captured)", "kernels": {}}
+    for path in paths:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        acc = defaultdict(list)
+        for r in rows[2:]:
+            acc[r[idx["Kernel Name"]]].append(r)
+        for name, rs in acc.items():
+            short = re.sub(r"\(.*", "", name).replace("void ", "")
+            get = lambda k: sum(_num(r[idx[k]], units[idx[k]]) for r in rs) / len(rs) if k in idx else None
+            out["kernels"][short] = {
+                "launches_captured": len(rs),
+                "time_ms": get("gpu__time_duration.sum"),
+                "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
+                "registers": get("launch__registers_per_thread"), "grid": get("launch__grid_size"),
+                "pipe_fma_cycles_active_pct": get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                "inst_executed_pipe_fma_pct": get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "inst_executed_pipe_xu_pct": get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "sm_clock_ghz": get("sm__cycles_elapsed.avg.per_second"),
+                "inst_executed": get("smsp__inst_executed.sum"),
+            }
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "json":
+        as_json(sys.argv[2], sys.argv[3:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
