@@ -115,6 +115,20 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
                              size_t workspace_bytes, void* stream);
 size_t spinn2d_poisson_residual_workspace_bytes(int N);
 
+/* ---- residual epilogues of the other BASELINE problem scripts (same contract as
+ * spinn2d_poisson_residual: *loss is ADDED to, workspace sized by
+ * spinn2d_poisson_residual_workspace_bytes):
+ *  ode3  (ode3.py:12-16, ode_base.py:83-92): res = u_xx + f(x), f the script's forcing with K = Kc
+ *        (0.01), loss = sum(res^2)/n_total; jets [3][N] -> gjets [3][N] of which ONLY row 2 (u_xx)
+ *        is written: pass present_mask 0x4 to spinn1d_jets_bwd.
+ *  cavity (cavity.py:84-100): K = 3 outputs (u, v, p), jets/gjets [5][N][3];
+ *        loss = sum_i (u_x+v_y)^2 + (u u_x + v u_y + p_x - nu lap u)^2 + (u v_x + v v_y + p_y - nu lap v)^2
+ *        (a sum over points, not a mean); all 15 entries of gjets are written. */
+int spinn1d_ode3_residual(int N, double n_total, const float* x, const float* jets, float Kc,
+                          float* gjets, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int spinn2d_cavity_residual(int N, float nu, const float* jets, float* gjets, float* loss,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the whole interior step of the stock Poisson residual in ONE call (K = 1):
  * what RegularPDE.interior_loss + loss.backward() compute (pde2d_base.py:132-141, common.py:242-248)
  * for res = scale*(u_xx + u_yy + amp*sin(kx x) sin(ky y) + f0), loss = sum(res^2)/n_total.

@@ -154,6 +154,39 @@ def poisson_interior_step(kind, x, y, xc, yc, h, W, b, n_total):
     return float(loss.detach())
 
 
+def ode3_interior_step(kind, x, xc, h, W, b, n_total, Kc=0.01):
+    """code/ode3.py:12-16 + code/ode_base.py:32-42,83-92: dense 1-D forward, two nested
+    autograd.grad, res = u_xx + f(x), loss = sum(res^2)/n_total, backward.  Returns the loss."""
+    u = forward1d(kind, x, xc, h, W, b).squeeze(-1)
+    (ux,) = _d(u, (x,))
+    (uxx,) = _d(ux, (x,))
+    f = -(Kc * (-6 * x + 4 / 3.) + x * (2 * x - 2. / 3) ** 2) * torch.exp(-(x - 1 / 3.) ** 2 / Kc) / Kc ** 2
+    res = uxx + f
+    loss = (res ** 2).sum() / n_total
+    loss.backward()
+    return float(loss.detach())
+
+
+def cavity_interior_step(kind, x, y, xc, yc, h, W, b, nu=0.01):
+    """code/cavity.py:84-100: U = nn(xs, ys) with 3 outputs; jets of u and v through
+    _compute_derivatives, gradient of p; continuity + two momentum residuals, SUMMED; backward."""
+    U = forward2d(kind, x, y, xc, yc, h, W, b)
+    u, v, p = U[:, 0], U[:, 1], U[:, 2]
+    ux, uy = _d(u, (x, y))
+    uxx, _ = _d(ux, (x, y))
+    _, uyy = _d(uy, (x, y))
+    vx, vy = _d(v, (x, y))
+    vxx, _ = _d(vx, (x, y))
+    _, vyy = _d(vy, (x, y))
+    px, py = _d(p, (x, y))
+    ce = ((ux + vy) ** 2).sum()
+    mex = ((u * ux + v * uy + px - nu * (uxx + uyy)) ** 2).sum()
+    mey = ((u * vx + v * vy + py - nu * (vxx + vyy)) ** 2).sum()
+    loss = ce + (mex + mey)
+    loss.backward()
+    return float(loss.detach())
+
+
 # --------------------------------------------------------------------------- #
 # nn.Module form of the same dense algorithm (same parameter names as the
 # reference: layer1.x/.y/.h, layer2.weight/.bias; 1-D layer1.center), so that the

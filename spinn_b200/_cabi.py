@@ -38,6 +38,9 @@ SIGNATURES = {
     "spinn2d_poisson_residual_workspace_bytes": (_c_size, [_c_int]),
     "spinn2d_poisson_residual": (_c_int, [_c_int, ctypes.c_double] + [_c_fp] * 3 + [ctypes.c_float] * 5
                                  + [_c_fp] * 3 + [_c_size, _c_fp]),
+    "spinn1d_ode3_residual": (_c_int, [_c_int, ctypes.c_double, _c_fp, _c_fp, ctypes.c_float, _c_fp, _c_fp, _c_fp,
+                                       _c_size, _c_fp]),
+    "spinn2d_cavity_residual": (_c_int, [_c_int, ctypes.c_float, _c_fp, _c_fp, _c_fp, _c_fp, _c_size, _c_fp]),
     "spinn2d_poisson_interior_step": (_c_int, [_c_int, _c_int, ctypes.c_double, _c_int, _c_int] + [_c_fp] * 7
                                       + [_c_int] + [_c_fp] * 2 + [ctypes.c_float] * 5 + [_c_fp] * 7
                                       + [_c_fp, _c_size, _c_fp, _c_size, _c_fp]),

@@ -104,6 +104,11 @@ class PDE:
         raise NotImplementedError()
 
 
+NO_LIVE_PLOT = ("live plotting (--plot) is out of scope of spinn_b200 (SURVEY.md section 2, row 11: "
+                "visualisation): run without --plot, or plug in your own Plotter subclass; error norms "
+                "(get_error) and result files (save) are provided")
+
+
 class Plotter:
     """Plot/err protocol (reference common.py:94-151); plotting itself is optional."""
 

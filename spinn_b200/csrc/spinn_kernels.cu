@@ -431,27 +431,24 @@ __device__ __forceinline__ float fwd_epilogue_tile(long long i0, int lim, int N,
 }
 
 // One span of the point set, walked in warp-tiles of 32*P consecutive points: tile `wt` of the span
-// starts at point `base + wt*32*P`; the span ends at `end`.  COOP: all warps of the CTA run the same
-// number of iterations (the multi-tile node loop has block-wide barriers).
-template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool COOP>
+// starts at point `base + wt*32*P`; the span ends at `end`.  The whole node table is in shared memory.
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL>
 __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N, const float* __restrict__ x,
-                                            const float* __restrict__ y, const float4* __restrict__ recs,
-                                            const float4* __restrict__ sm4w, float4* __restrict__ sm4, int npairs,
-                                            int tile_pairs, float b0, float* __restrict__ jets, bool vec,
-                                            long long gw, long long nwarps) {
+                                            const float* __restrict__ y, const float4* __restrict__ sm4, int npairs,
+                                            float b0, float* __restrict__ jets, bool vec, long long gw,
+                                            long long nwarps) {
   constexpr int NJ = MIXED ? 6 : 5;
   const int lane = threadIdx.x & 31;
   const long long nwt = (end - base + 32 * P - 1) / (32 * P);
   const long long iters = (nwt + nwarps - 1) / nwarps;
   for (long long it = 0; it < iters; ++it) {
     const long long wt = gw + it * nwarps;
-    const bool active = wt < nwt;                  // warp-uniform
-    if (!COOP && !active) break;
+    if (wt >= nwt) break;                          // warp-uniform; no block-level syncs on this path
     const long long i0 = base + (wt * 32 + lane) * P;
     const int lim = (int)end;                      // points at or beyond `end` belong to another span
     float px[P], py[P];
-    load_points<P>(x, active ? i0 : (long long)lim, lim, vec, px);
-    load_points<P>(y, active ? i0 : (long long)lim, lim, vec, py);
+    load_points<P>(x, i0, lim, vec, px);
+    load_points<P>(y, i0, lim, vec, py);
     float2 x2[P], y2[P], acc[P][NJ];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
@@ -460,16 +457,68 @@ __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N
 #pragma unroll
       for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
     }
-    if (!COOP) {
-      k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4w, npairs, x2, y2, acc);
-    } else {
-      for (int t0 = 0; t0 < npairs; t0 += tile_pairs) {
-        const int n = min(tile_pairs, npairs - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < 3 * n; e += THREADS) sm4[e] = recs[3 * (size_t)t0 + e];
-        __syncthreads();
-        k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4, n, x2, y2, acc);
-      }
+    k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4, npairs, x2, y2, acc);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      float out[P];
+#pragma unroll
+      for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
+      // `lim` (not N) bounds the stores of this span; the jets rows are N long
+      store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
+    }
+  }
+}
+
+// The same walk when the node table does not fit shared memory (more than 4096 nodes): every
+// warp-tile of points streams ALL node-record tiles through a 2-stage ring filled by TMA bulk copies
+// -- tile g+1 is in flight while tile g is consumed; one block-wide barrier per tile hands the
+// consumed stage back to the producer (thread 0), so all warps of the CTA run the same number of
+// iterations (inactive ones on dummy points).
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL>
+__device__ __forceinline__ void k1_fwd_span_multi(int N, const float* __restrict__ x, const float* __restrict__ y,
+                                                  const float4* __restrict__ recs, float4* __restrict__ sm4,
+                                                  int npairs, int tile_pairs, float b0, float* __restrict__ jets,
+                                                  bool vec, long long gw, long long nwarps, uint64_t* fullb) {
+  constexpr int NJ = MIXED ? 6 : 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwt = ((long long)N + 32 * P - 1) / (32 * P);
+  const long long iters = (nwt + nwarps - 1) / nwarps;
+  const int ntile = (npairs + tile_pairs - 1) / tile_pairs;
+  const long long total = iters * ntile;
+  long long g = 0;
+  auto issue = [&](long long gi) {                 // thread 0 only
+    const int t = (int)(gi % ntile), st = (int)(gi & 1);
+    const int n = min(tile_pairs, npairs - t * tile_pairs);
+    const unsigned bytes = 3u * (unsigned)n * (unsigned)sizeof(float4);
+    mbar_expect_tx(&fullb[st], bytes);
+    for (unsigned off = 0; off < bytes; off += TMA_CHUNK)
+      tma_bulk_g2s(reinterpret_cast<char*>(sm4 + (size_t)st * 3 * tile_pairs) + off,
+                   reinterpret_cast<const char*>(recs + 3 * (size_t)t * tile_pairs) + off,
+                   min(TMA_CHUNK, bytes - off), &fullb[st]);
+  };
+  if (threadIdx.x == 0 && total > 0) issue(0);
+  for (long long it = 0; it < iters; ++it) {
+    const long long wt = gw + it * nwarps;
+    const bool active = wt < nwt;                  // warp-uniform
+    const long long i0 = (wt * 32 + lane) * P;
+    float px[P], py[P];
+    load_points<P>(x, active ? i0 : (long long)N, N, vec, px);
+    load_points<P>(y, active ? i0 : (long long)N, N, vec, py);
+    float2 x2[P], y2[P], acc[P][NJ];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      x2[q] = f2dup(px[q]);
+      y2[q] = f2dup(py[q]);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) acc[q][a] = f2(0.f, 0.f);
+    }
+    for (int t = 0; t < ntile; ++t, ++g) {
+      const int st = (int)(g & 1);
+      const int n = min(tile_pairs, npairs - t * tile_pairs);
+      if (threadIdx.x == 0 && g + 1 < total) issue(g + 1);        // stage st^1 was released by the barrier below
+      mbar_wait(&fullb[st], (unsigned)((g >> 1) & 1));
+      k1_fwd_inner<KIND, P, MIXED, UNROLL>(sm4 + (size_t)st * 3 * tile_pairs, n, x2, y2, acc);
+      __syncthreads();                                            // everyone is done reading stage st
     }
     if (active) {
 #pragma unroll
@@ -477,8 +526,7 @@ __device__ __forceinline__ void k1_fwd_span(long long base, long long end, int N
         float out[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) out[q] = acc[q][a].x + acc[q][a].y + (a == 0 ? b0 : 0.f);
-        // `lim` (not N) bounds the stores of this span; the jets rows are N long
-        store_points<P>(jets + (size_t)a * N, i0, lim, vec, out);
+        store_points<P>(jets + (size_t)a * N, i0, N, vec, out);
       }
     }
   }
@@ -503,7 +551,7 @@ __device__ __forceinline__ float k1_fwd_epilogue_span(long long base, long long 
 // the remainder -- less than one round -- is walked with one point per thread (tiles of 32 points), so
 // that the last, partial round keeps (nearly) every warp of every SM busy at half the work instead of
 // leaving half of the warps idle (8-GPU shards: 3.46 rounds -> 3 rounds + one half-size round).
-template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool EPI>
+template <int KIND, int P, bool MIXED, int THREADS, int UNROLL, bool EPI, bool MULTI>
 __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, const float* __restrict__ y,
                                             const float4* __restrict__ recs, int npairs, int tile_pairs,
                                             const float* __restrict__ bias, float* __restrict__ jets,
@@ -514,7 +562,7 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
   const int lw = threadIdx.x >> 5;
   const long long gw = (long long)(lw >> 2) * ((long long)gridDim.x * 4) + (long long)blockIdx.x * 4 + (lw & 3);
   const long long nwarps = (long long)gridDim.x * WPC;
-  const bool single = npairs <= tile_pairs;
+  constexpr bool single = !MULTI;                  // MULTI: node table larger than shared memory (own kernel)
   const bool vec = vec_ok != 0;
   const float b0 = bias ? bias[0] : 0.f;
   float lsum = 0.f;                                // EPI: this thread's share of sum res^2
@@ -537,18 +585,23 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
     mbar_wait(&bar, 0);
     const long long round_pts = nwarps * 32 * P;
     const long long main_end = P == 1 ? (long long)N : ((long long)N / round_pts) * round_pts;
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, false>(0, main_end, N, x, y, recs, sm4, sm4, npairs, tile_pairs,
-                                                        b0, jets, vec, gw, nwarps);
+    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL>(0, main_end, N, x, y, sm4, npairs, b0, jets, vec, gw, nwarps);
     if (P > 1 && main_end < N)
-      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL, false>(main_end, N, N, x, y, recs, sm4, sm4, npairs,
-                                                          tile_pairs, b0, jets, vec, gw, nwarps);
+      k1_fwd_span<KIND, 1, MIXED, THREADS, UNROLL>(main_end, N, N, x, y, sm4, npairs, b0, jets, vec, gw, nwarps);
     if (EPI) {
       lsum = k1_fwd_epilogue_span<KIND, P>(0, main_end, N, x, y, jets, gw, nwarps, ep);
       if (P > 1 && main_end < N) lsum += k1_fwd_epilogue_span<KIND, 1>(main_end, N, N, x, y, jets, gw, nwarps, ep);
     }
   } else {
-    k1_fwd_span<KIND, P, MIXED, THREADS, UNROLL, true>(0, N, N, x, y, recs, sm4, sm4, npairs, tile_pairs, b0,
-                                                       jets, vec, gw, nwarps);
+    __shared__ __align__(8) uint64_t fullb[2];
+    if (threadIdx.x == 0) {
+      mbar_init(&fullb[0], 1);
+      mbar_init(&fullb[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    k1_fwd_span_multi<KIND, P, MIXED, THREADS, UNROLL>(N, x, y, recs, sm4, npairs, tile_pairs, b0, jets, vec, gw,
+                                                       nwarps, fullb);
     if (EPI) lsum = k1_fwd_epilogue_span<KIND, P>(0, N, N, x, y, jets, gw, nwarps, ep);
   }
   if (EPI) {                                       // one loss partial per warp, every warp writes its slot
@@ -559,23 +612,23 @@ __device__ __forceinline__ void k1_fwd_body(int N, const float* __restrict__ x, 
 }
 
 // EPI: the forward also runs the Poisson residual epilogue (FwdEpilogue) on its jets
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI>
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI, bool MULTI>
 __global__ void __launch_bounds__(THREADS, MINB)
 g2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
                 const float* __restrict__ bias, float* __restrict__ jets, int vec_ok, const FwdEpilogue ep) {
   extern __shared__ float4 sm4[];
-  k1_fwd_body<GAUSSIAN, P, MIXED, THREADS, UNROLL, EPI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
+  k1_fwd_body<GAUSSIAN, P, MIXED, THREADS, UNROLL, EPI, MULTI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
 }
 
 // the same persistent, TMA-staged forward with the softplus-hat pair function (spinn_math.cuh, FAST PATH 2)
-template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI>
+template <int P, bool MIXED, int THREADS, int MINB, int UNROLL, bool EPI, bool MULTI>
 __global__ void __launch_bounds__(THREADS, MINB)
 s2k1_fwd_kernel(int N, const float* __restrict__ x, const float* __restrict__ y,
                 const float4* __restrict__ recs, int npairs, int tile_pairs,
                 const float* __restrict__ bias, float* __restrict__ jets, int vec_ok, const FwdEpilogue ep) {
   extern __shared__ float4 sm4[];
-  k1_fwd_body<SOFTPLUS, P, MIXED, THREADS, UNROLL, EPI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
+  k1_fwd_body<SOFTPLUS, P, MIXED, THREADS, UNROLL, EPI, MULTI>(N, x, y, recs, npairs, tile_pairs, bias, jets, vec_ok, sm4, ep);
 }
 
 // -----------------------------------------------------------------------------
@@ -1120,6 +1173,62 @@ poisson_residual_kernel(int N, float inv_n, const float* __restrict__ x, const f
   }
 }
 
+// ode3 residual epilogue (1-D, K=1): jets [3][N] -> gjets row 2 (u_xx) only (rows 0, 1 are absent:
+// present_mask 0x4), loss partials
+__global__ void __launch_bounds__(256)
+ode3_residual_kernel(int N, float inv_n, float Kc, const float* __restrict__ x, const float* __restrict__ jets,
+                     float* __restrict__ gj, float* __restrict__ lpart) {
+  __shared__ float red[8];
+  const size_t n = (size_t)N;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float res = jets[2 * n + i] + ode3_forcing(x[i], Kc);
+    s = fmaf(res, res, s);
+    gj[2 * n + i] = 2.f * res * inv_n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    lpart[blockIdx.x] = v * inv_n;
+  }
+}
+
+// cavity residual epilogue (2-D, K=3: u, v, p): jets [5][N][3] -> gjets [5][N][3], loss partials
+__global__ void __launch_bounds__(256)
+cavity_residual_kernel(int N, float nu, const float* __restrict__ jets, float* __restrict__ gj,
+                       float* __restrict__ lpart) {
+  __shared__ float red[8];
+  const size_t n = (size_t)N;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    float J[5][3], g[5][3];
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) J[a][k] = jets[(a * n + i) * 3 + k];
+    s += cavity_residual_point(J, nu, g);
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gj[(a * n + i) * 3 + k] = g[a][k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    lpart[blockIdx.x] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 add_partials_kernel(int n, const float* __restrict__ part, float* __restrict__ out) {
   __shared__ double red[256];
@@ -1193,8 +1302,8 @@ struct FastFwdArgs {
   int* nwarps_out;             // EPI: number of loss partials written (= warps of the grid)
 };
 
-template <int KIND, int P, int T, int B, int U, bool MIXED, bool EPI>
-static int launch_fast_fwd_e(const FastFwdArgs& a) {
+template <int KIND, int P, int T, int B, int U, bool MIXED, bool EPI, bool MULTI>
+static int launch_fast_fwd_k(const FastFwdArgs& a) {
   const long long nwt = ((long long)a.N + 32 * P - 1) / (32 * P);
   long long blocks = (nwt + (T / 32) - 1) / (T / 32);
   if (blocks > (long long)a.sms * B) blocks = (long long)a.sms * B;
@@ -1202,16 +1311,22 @@ static int launch_fast_fwd_e(const FastFwdArgs& a) {
   if (EPI && a.nwarps_out) *a.nwarps_out = (int)blocks * (T / 32);
   static OnceFlags once;
   if (KIND == GAUSSIAN) {
-    auto kfn = g2k1_fwd_kernel<P, MIXED, T, B, U, EPI>;
+    auto kfn = g2k1_fwd_kernel<P, MIXED, T, B, U, EPI, MULTI>;
     CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
     kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok, ep);
   } else {
-    auto kfn = s2k1_fwd_kernel<P, MIXED, T, B, U, EPI>;
+    auto kfn = s2k1_fwd_kernel<P, MIXED, T, B, U, EPI, MULTI>;
     CUDA_TRY(opt_in_smem_once(once, a.dev, kfn, 98304));
     kfn<<<(int)blocks, T, a.smem, a.s>>>(a.N, a.x, a.y, a.recs, a.npairs, a.tile_pairs, a.bias, a.jets, a.vec_ok, ep);
   }
   LAUNCH_CHECK(KIND == GAUSSIAN ? "g2k1_fwd_kernel" : "s2k1_fwd_kernel");
   return SPINN_OK;
+}
+template <int KIND, int P, int T, int B, int U, bool MIXED, bool EPI>
+static int launch_fast_fwd_e(const FastFwdArgs& a) {
+  // the multi-tile kernel exists for the default tile shape only (node sets > 4096 are rare)
+  if (a.npairs > a.tile_pairs) return launch_fast_fwd_k<KIND, 2, 256, 2, 2, MIXED, EPI, true>(a);
+  return launch_fast_fwd_k<KIND, P, T, B, U, MIXED, EPI, false>(a);
 }
 template <int KIND, int P, int T, int B, int U>
 static int launch_fast_fwd(bool mixed, const FastFwdArgs& a) {
@@ -1472,8 +1587,11 @@ static int jets_fwd_impl(int dim, int kind, int level, int N, int M_free, int M_
       pack_nodes_k1fwd_kernel<SOFTPLUS><<<ceil_div_i(p.npairs, 128), 128, 0, s>>>(M, M_free, p.npairs, xf, yf,
                                                                                   xfix, yfix, h, hs, W, recs);
     LAUNCH_CHECK("pack_nodes_k1fwd_kernel");
-    const int tile_pairs = p.npairs < 2048 ? p.npairs : 2048;
-    const size_t smem = (size_t)3 * tile_pairs * sizeof(float4);
+    // node table: one stage when it fits 96 KB of shared memory (<= 2048 node pairs), else a 2-stage
+    // ring of 1024-pair tiles (same 96 KB)
+    const bool one_stage = p.npairs <= 2048;
+    const int tile_pairs = one_stage ? p.npairs : 1024;
+    const size_t smem = (size_t)3 * tile_pairs * sizeof(float4) * (one_stage ? 1 : 2);
     const int vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)jets) % 16 == 0) && (N % 4 == 0);
     const bool mixed = level == 3;
     const Tune tune = get_tune();
@@ -1733,6 +1851,42 @@ int spinn2d_poisson_residual(int N, double n_total, const float* x, const float*
   poisson_residual_kernel<<<blocks, 256, 0, s>>>(N, (float)(1.0 / n_total), x, y, jets, scale, amp, kx,
                                                  ky, f0, gjets, lpart);
   LAUNCH_CHECK("poisson_residual_kernel");
+  add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
+  LAUNCH_CHECK("add_partials_kernel");
+  return SPINN_OK;
+}
+
+int spinn1d_ode3_residual(int N, double n_total, const float* x, const float* jets, float Kc, float* gjets,
+                          float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N < 0 || n_total <= 0.0 || !(Kc > 0.f)) return fail(SPINN_E_BADARG, "bad N/n_total/K");
+  if (N == 0) return SPINN_OK;
+  if (!x || !jets || !gjets || !loss) return fail(SPINN_E_BADARG, "null pointer in ode3_residual");
+  if (!workspace || workspace_bytes < spinn2d_poisson_residual_workspace_bytes(N))
+    return fail(SPINN_E_WORKSPACE, "residual workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = ceil_div_i(N, 256);
+  if (blocks > 1024) blocks = 1024;
+  float* lpart = (float*)workspace;
+  ode3_residual_kernel<<<blocks, 256, 0, s>>>(N, (float)(1.0 / n_total), Kc, x, jets, gjets, lpart);
+  LAUNCH_CHECK("ode3_residual_kernel");
+  add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
+  LAUNCH_CHECK("add_partials_kernel");
+  return SPINN_OK;
+}
+
+int spinn2d_cavity_residual(int N, float nu, const float* jets, float* gjets, float* loss, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (N < 0) return fail(SPINN_E_BADARG, "bad N");
+  if (N == 0) return SPINN_OK;
+  if (!jets || !gjets || !loss) return fail(SPINN_E_BADARG, "null pointer in cavity_residual");
+  if (!workspace || workspace_bytes < spinn2d_poisson_residual_workspace_bytes(N))
+    return fail(SPINN_E_WORKSPACE, "residual workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = ceil_div_i(N, 256);
+  if (blocks > 1024) blocks = 1024;
+  float* lpart = (float*)workspace;
+  cavity_residual_kernel<<<blocks, 256, 0, s>>>(N, nu, jets, gjets, lpart);
+  LAUNCH_CHECK("cavity_residual_kernel");
   add_partials_kernel<<<1, 256, 0, s>>>(blocks, lpart, loss);
   LAUNCH_CHECK("add_partials_kernel");
   return SPINN_OK;

@@ -394,7 +394,8 @@ SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* d
 // factor q^-1 = EK^-1/4 so that R = 1/(A_x' A_y') squares to EK/(A_x A_y)^2 without an extra multiply.
 // The series branches of the generic path (log1p / 1-e for small arguments) are not needed at the
 // level of the SUMS over nodes / points: their absolute errors (~1e-7 of the largest term) are
-// those of fp32 rounding; `LOGFIX` adds the first-order correction of the rounding of 1+w.
+// those of fp32 rounding; s2_log2_1pw adds the first-order correction of the rounding of 1+w (what
+// is left in u is MUFU.LG2's own absolute error, 2^-22.6 per node).
 // =============================================================================
 constexpr float HAT_Q_F    = 2.568050838266732f;       // EK2^(1/4)
 constexpr float HAT_IQ_F   = 0.3894003907940293f;      // 1/q
@@ -422,7 +423,7 @@ SP_HD S2FwdNode s2_fwd_node(float c, float d, float h, float W) {
 }
 
 // shared head of forward and backward: X, Y, e_x, e_y, A_x', A_y', R, 1+w, i, sigma
-struct S2Head { float2 X, Y, ex, ey, Ax, Ay, R, opw, i, sg; };
+struct S2Head { float2 X, Y, ex, ey, Ax, Ay, R, w, opw, i, sg; };
 SP_HD S2Head s2_head(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1) {
   const float2 iq = f2dup(HAT_IQ_F), one = f2dup(1.0f);
   S2Head h;
@@ -432,11 +433,20 @@ SP_HD S2Head s2_head(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1) {
   h.Ax = f2fma(h.ex, iq, iq); h.Ay = f2fma(h.ey, iq, iq);
   h.R = f2rcp(f2mul(h.Ax, h.Ay));
   const float2 ee = f2mul(h.ex, h.ey), R2 = f2mul(h.R, h.R);
-  const float2 w = f2mul(ee, R2);
-  h.opw = f2add(w, one);
+  h.w = f2mul(ee, R2);
+  h.opw = f2add(h.w, one);
   h.i = f2rcp(h.opw);
-  h.sg = f2mul(w, h.i);
+  h.sg = f2mul(h.w, h.i);
   return h;
+}
+
+// log2(1+w) from MUFU.LG2 of the ROUNDED sum u = fl(1+w), plus the first-order correction for that
+// rounding: ln(1+w) = ln u + (w - (u-1))/u  (u-1 and w-(u-1) are exact in fp32; 1/u = i is at hand).
+// 4 packed instructions; on the MUFU-bound forward they ride in spare FP32 slots.
+SP_HD float2 s2_log2_1pw(const S2Head& h) {
+  const float2 um1 = f2add(h.opw, f2dup(-1.0f));
+  const float2 d = f2fma(um1, f2dup(-1.0f), h.w);
+  return f2fma(f2mul(d, h.i), f2dup(LOG2E_F), f2lg2(h.opw));
 }
 
 // acc: u, ux, uy, uxx, uyy (, uxy); lanes = partial sums over one node parity
@@ -445,7 +455,7 @@ SP_HD void s2_fwd_pair(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1, fl
                        float2 w2, float2* acc) {
   const float2 one = f2dup(1.0f), neg1 = f2dup(-1.0f);
   const S2Head h = s2_head(x2, y2, nc, nd, c1);
-  acc[0] = f2fma(w0, f2lg2(h.opw), acc[0]);
+  acc[0] = f2fma(w0, s2_log2_1pw(h), acc[0]);
   const float2 omx = f2fma(h.ex, neg1, one), omy = f2fma(h.ey, neg1, one);
   const float2 Tx = f2mul(omx, f2mul(h.Ay, h.R)), Ty = f2mul(omy, f2mul(h.Ax, h.R));   // q tanh
   const float2 e1 = f2mul(w1, h.sg);
@@ -499,7 +509,7 @@ SP_HD void s2_bwd_pair(float2 x2, float2 y2, float2 g0, float2 g1, float2 g2, fl
   float2 mdc = zero, mdd = zero, B1 = zero, A2 = zero;
   bool hc = false, hd = false, hb = false, ha = false;
   if (H0) {
-    acc[4] = f2fma(g0, f2lg2(h.opw), acc[4]);
+    acc[4] = f2fma(g0, s2_log2_1pw(h), acc[4]);
     s2_term(hc, mdc, g0, t);
     s2_term(hd, mdd, g0, v);
   }
@@ -549,6 +559,36 @@ SP_HD void s2_bwd_finish(float h, float W, const float* a, float* dW, float* dc,
   *dc = (float)(-(double)W * iF * (double)a[1]);
   *dd = (float)(-(double)W * iF * (double)a[2]);
   *dh = (float)(-(double)W * r * iF * (double)a[3]);
+}
+
+// =============================================================================
+// Per-point residual epilogues of the BASELINE problem scripts: residual, its
+// contribution to the loss, and dLoss/dJets -- what autograd hands the fused backward.
+// =============================================================================
+// ode3 (code/ode3.py:12-16): res = u_xx + f(x), K = 0.01;  loss = mean(res^2) (ode_base.py:90-92)
+SP_HD float ode3_forcing(float x, float Kc) {
+  const float d = x - (1.0f / 3.0f);
+  const float t = 2.0f * x - (2.0f / 3.0f);
+  return -(Kc * (-6.0f * x + (4.0f / 3.0f)) + x * t * t) * expf(-d * d / Kc) / (Kc * Kc);
+}
+
+// cavity (code/cavity.py:84-100): J[a][k], a in {.,x,y,xx,yy}, k in {u,v,p}; nu = 0.01
+//   ce = (u_x + v_y)^2,  mex = (u u_x + v u_y + p_x - nu (u_xx+u_yy))^2,  mey likewise for v;
+//   loss = sum over points of ce + mex + mey  (a SUM, not a mean).  g[a][k] = d(point loss)/dJ[a][k].
+SP_HD float cavity_residual_point(const float (*J)[3], float nu, float (*g)[3]) {
+  const float u = J[0][0], v = J[0][1];
+  const float ux = J[1][0], vx = J[1][1], px = J[1][2];
+  const float uy = J[2][0], vy = J[2][1], py = J[2][2];
+  const float c = ux + vy;
+  const float a = u * ux + v * uy + px - nu * (J[3][0] + J[4][0]);
+  const float b = u * vx + v * vy + py - nu * (J[3][1] + J[4][1]);
+  const float a2 = 2.0f * a, b2 = 2.0f * b, c2 = 2.0f * c;
+  g[0][0] = a2 * ux + b2 * vx;  g[0][1] = a2 * uy + b2 * vy;  g[0][2] = 0.f;
+  g[1][0] = c2 + a2 * u;        g[1][1] = b2 * u;             g[1][2] = a2;
+  g[2][0] = a2 * v;             g[2][1] = c2 + b2 * v;        g[2][2] = b2;
+  g[3][0] = -nu * a2;           g[3][1] = -nu * b2;           g[3][2] = 0.f;
+  g[4][0] = -nu * a2;           g[4][1] = -nu * b2;           g[4][2] = 0.f;
+  return c * c + a * a + b * b;
 }
 
 // number of jets / upstream-gradient slots per "level"

@@ -156,3 +156,110 @@ class PoissonInteriorStep:
         if l2.bias is not None:
             l2.bias.grad = p.view("d_b")
         return p.view("loss")
+
+
+class _ResidualStep:
+    """Shared plumbing of the device-resident interior steps below: forward jets -> residual
+    epilogue (loss + dLoss/dJets) -> fused backward into a GradPack, all through the C ABI with
+    preallocated buffers."""
+
+    LAUNCHES = 8        # pack_nodes, fwd, residual, add_partials, pack_nodes, bwd, (bias_partial,) finalize
+
+    def _setup(self, nn, dim, n_points, n_jets, K):
+        self.lib = _cabi.load()
+        self.nn = nn
+        l1, l2 = nn.layer1, nn.layer2
+        free = l1.x if dim == 2 else l1.center
+        fixed = l1.xf if dim == 2 else l1.fixed
+        self.Mf, self.Mx = free.numel(), fixed.numel()
+        M = self.Mf + self.Mx
+        dev = free.device
+        self.N, self.K = n_points, K
+        self.pack = GradPack(dim, self.Mf, M, K, l1.h.numel(), l2.bias is not None, dev)
+        self.jets = torch.empty((n_jets, n_points, K), dtype=torch.float32, device=dev)
+        self.gjets = torch.zeros((n_jets, n_points, K), dtype=torch.float32, device=dev)
+        fws = self.lib.spinn2d_fwd_workspace_bytes if dim == 2 else self.lib.spinn1d_fwd_workspace_bytes
+        bws = self.lib.spinn2d_bwd_workspace_bytes if dim == 2 else self.lib.spinn1d_bwd_workspace_bytes
+        self.ws_f = torch.empty(fws(n_points, M, K), dtype=torch.uint8, device=dev)
+        self.ws_b = torch.empty(bws(n_points, M, K), dtype=torch.uint8, device=dev)
+        self.ws_r = torch.empty(self.lib.spinn2d_poisson_residual_workspace_bytes(n_points), dtype=torch.uint8,
+                                device=dev)
+
+    def assign_grads(self):
+        l1, l2, p = self.nn.layer1, self.nn.layer2, self.pack
+        if p.dim == 2:
+            l1.x.grad, l1.y.grad = p.view("d_x"), p.view("d_y")
+        else:
+            l1.center.grad = p.view("d_x")
+        l1.h.grad = p.view("d_h").reshape(l1.h.shape)
+        l2.weight.grad = p.view("d_W").reshape(l2.weight.shape)
+        if l2.bias is not None:
+            l2.bias.grad = p.view("d_b")
+        return p.view("loss")
+
+
+class Ode3InteriorStep(_ResidualStep):
+    """BASELINE config 1 (code/ode3.py:12-16, code/ode_base.py:83-92): 1-D jets (u, u_x, u_xx) ->
+    res = u_xx + f(x), loss = sum(res^2)/n_total -> backward with only the u_xx row present."""
+
+    def __init__(self, nn, x, n_total=None, Kc=0.01):
+        self.x = x.detach().contiguous()
+        self._setup(nn, 1, self.x.numel(), 3, 1)
+        self.n_total = float(self.N if n_total is None else n_total)
+        self.Kc = float(Kc)
+
+    def run(self, all_reduce=True):
+        lib, nn, p, s = self.lib, self.nn, self.pack, _stream()
+        l1, l2 = nn.layer1, nn.layer2
+        hs = int(l1.h.numel() == 1)
+        p.view("loss").zero_()
+        rc = lib.spinn1d_jets_fwd(nn.kind, 2, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(l1.center),
+                                  _ptr(l1.fixed), _ptr(l1.h), hs, _ptr(l2.weight), _ptr(l2.bias), _ptr(self.jets),
+                                  _ptr(self.ws_f), self.ws_f.numel(), s)
+        _cabi.check(rc, "spinn1d_jets_fwd")
+        rc = lib.spinn1d_ode3_residual(self.N, self.n_total, _ptr(self.x), _ptr(self.jets), self.Kc,
+                                       _ptr(self.gjets), _ptr(p.view("loss")), _ptr(self.ws_r), self.ws_r.numel(), s)
+        _cabi.check(rc, "spinn1d_ode3_residual")
+        rc = lib.spinn1d_jets_bwd(nn.kind, 2, 0x4, self.N, self.Mf, self.Mx, 1, _ptr(self.x), _ptr(l1.center),
+                                  _ptr(l1.fixed), _ptr(l1.h), hs, _ptr(l2.weight), _ptr(self.gjets),
+                                  _ptr(p.view("d_x")), _ptr(p.view("d_h")), _ptr(p.view("d_W")),
+                                  _ptr(p.view("d_b")) if p.has("d_b") else None, _ptr(self.ws_b),
+                                  self.ws_b.numel(), s)
+        _cabi.check(rc, "spinn1d_jets_bwd")
+        if all_reduce:
+            p.all_reduce()
+        return p.flat
+
+
+class CavityInteriorStep(_ResidualStep):
+    """BASELINE config 4 (code/cavity.py:84-100): 2-D jets of the three outputs (u, v, p) ->
+    continuity + momentum residuals, summed over the points -> backward with all 5 rows."""
+
+    def __init__(self, nn, x, y, nu=0.01):
+        if nn.layer2.weight.shape[0] != 3:
+            raise ValueError("CavityInteriorStep needs the 3-output network (u, v, p)")
+        self.x, self.y = x.detach().contiguous(), y.detach().contiguous()
+        self._setup(nn, 2, self.x.numel(), 5, 3)
+        self.nu = float(nu)
+
+    def run(self, all_reduce=True):
+        lib, nn, p, s = self.lib, self.nn, self.pack, _stream()
+        l1, l2 = nn.layer1, nn.layer2
+        hs = int(l1.h.numel() == 1)
+        p.view("loss").zero_()
+        rc = lib.spinn2d_jets_fwd(nn.kind, 2, self.N, self.Mf, self.Mx, 3, _ptr(self.x), _ptr(self.y), _ptr(l1.x),
+                                  _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs, _ptr(l2.weight),
+                                  _ptr(l2.bias), _ptr(self.jets), _ptr(self.ws_f), self.ws_f.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_fwd")
+        rc = lib.spinn2d_cavity_residual(self.N, self.nu, _ptr(self.jets), _ptr(self.gjets), _ptr(p.view("loss")),
+                                         _ptr(self.ws_r), self.ws_r.numel(), s)
+        _cabi.check(rc, "spinn2d_cavity_residual")
+        rc = lib.spinn2d_jets_bwd(nn.kind, 2, 0, self.N, self.Mf, self.Mx, 3, _ptr(self.x), _ptr(self.y), _ptr(l1.x),
+                                  _ptr(l1.y), _ptr(l1.xf), _ptr(l1.yf), _ptr(l1.h), hs, _ptr(l2.weight),
+                                  _ptr(self.gjets), _ptr(p.view("d_x")), _ptr(p.view("d_y")), _ptr(p.view("d_h")),
+                                  _ptr(p.view("d_W")), _ptr(p.view("d_b")) if p.has("d_b") else None,
+                                  _ptr(self.ws_b), self.ws_b.numel(), s)
+        _cabi.check(rc, "spinn2d_jets_bwd")
+        if all_reduce:
+            p.all_reduce()
+        return p.flat

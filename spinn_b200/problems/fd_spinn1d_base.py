@@ -42,29 +42,6 @@ class FDPlotter1D(Plotter1D):
         diff = self._exact_at_next_level(xn) - pn
         return np.mean(np.abs(diff)), np.sqrt(np.mean(diff ** 2)), np.max(np.abs(diff))
 
-    def plot_solution(self):
-        import matplotlib.pyplot as plt
-        xn, pn = self.get_plot_data()
-        pde = self.pde
-        exact = self.show_exact and pde.has_exact()
-        if self.plt1 is None:
-            (self.plt1,) = plt.plot(xn, pn, "-", label="computed")
-            self.title = plt.title(f"t = {pde.t:.3e} seconds")
-            if exact:
-                yn = self._exact_at_next_level(xn)
-                (self.lexact,) = plt.plot(xn, yn, label="exact")
-            else:
-                yn = pde.u0.detach().cpu().numpy()
-            plt.grid()
-            pad = 0.2 * (np.max(yn) - np.min(yn))
-            plt.ylim(np.min(yn) - pad, np.max(yn) + pad)
-        else:
-            self.title.set_text(f"t = {pde.t:.3e} seconds")
-            self.plt1.set_data(xn, pn)
-            if exact:
-                self.lexact.set_data(xn, self._exact_at_next_level(xn))
-        return self.get_error(xn, pn)
-
     def save(self, dirname):
         it, t = self.pde.iter, self.pde.t
         torch.save(self.nn.state_dict(), os.path.join(dirname, "model_%04d.pt" % it))
@@ -185,6 +162,3 @@ class AppFD1D(App1D):
             print("Current time: %f" % self.pde.t)
             if (level + 1) % self.pde.t_skip == 0 and out_dir is not None:
                 self.plotter.save(out_dir)
-        if self.solver.plot:
-            import matplotlib.pyplot as plt
-            plt.show()

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .common import App, Plotter, add_flags, tensor
+from .common import NO_LIVE_PLOT, App, Plotter, add_flags, tensor
 
 
 def gaussian(x):
@@ -148,50 +148,11 @@ class Plotter1D(Plotter):
         x = self.pde.plot_points()
         return x, self.nn(tensor(x)).detach().cpu().numpy()
 
-    # live plotting (--plot; needs matplotlib): plot() = plot_solution() then plot_weights(), both
-    # overridable as in the reference (spinn1d.py:44-83)
-    def plot_solution(self):
-        import matplotlib.pyplot as plt
-        xn, pn = self.get_plot_data()
-        if self.plt1 is not None:
-            self.plt1.set_data(xn, pn)
-            return self.get_error(xn, pn)
-        (self.plt1,) = plt.plot(xn, pn, "-", label="computed")
-        shown = pn
-        if self.show_exact and self.pde.has_exact():
-            shown = self.pde.exact(xn)
-            plt.plot(xn, shown, label="exact")
-        pad = 0.5 * (np.max(shown) - np.min(shown))
-        plt.grid()
-        plt.xlim(-0.1, 1.1)
-        plt.ylim(np.min(shown) - pad, np.max(shown) + pad)
-        return self.get_error(xn, pn)
-
-    def plot_weights(self):
-        import matplotlib.pyplot as plt
-        centres = self.nn.centers().detach().cpu().numpy()
-        if self.plt2 is None:
-            (self.plt2,) = plt.plot(centres, np.zeros_like(centres), "o", label="centers")
-        else:
-            self.plt2.set_data(centres, np.zeros_like(centres))
-
+    # live plotting is not provided (the reference's matplotlib code, spinn1d.py:44-83, is visualisation)
     def plot(self):
-        import matplotlib.pyplot as plt
-        fresh = self.plt1 is None
-        err = self.plot_solution()
-        self.plot_weights()
-        if fresh:
-            plt.legend()
-            plt.pause(0.001)
-        else:
-            canvas = plt.gcf().canvas
-            canvas.draw()
-            canvas.flush_events()
-        return err
+        raise NotImplementedError(NO_LIVE_PLOT)
 
-    def show(self):
-        import matplotlib.pyplot as plt
-        plt.show()
+    plot_solution = plot_weights = plot
 
 
 class App1D(App):

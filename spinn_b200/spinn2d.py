@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .common import App, Plotter, add_flags, tensor
+from .common import NO_LIVE_PLOT, App, Plotter, add_flags, tensor
 
 
 def gaussian(x, y):
@@ -185,8 +185,7 @@ class SPINN2D(nn.Module):
 
 
 class Plotter2D(Plotter):
-    """Error norms and result files (reference spinn2d.py:11-94).  Live plotting needs
-    mayavi, imported lazily only if ``--plot`` is used."""
+    """Error norms and result files (reference spinn2d.py:11-43); no live plotting."""
 
     def get_error(self, xn=None, yn=None, pn=None):
         if not self.pde.has_exact():
@@ -207,39 +206,11 @@ class Plotter2D(Plotter):
         pn.shape = x.shape
         return x, y, pn
 
-    def plot_solution(self):
-        from mayavi import mlab
-        xn, yn, pn = self.get_plot_data()
-        if self.plt1 is None:
-            mlab.figure(size=(700, 700), fgcolor=(0, 0, 0), bgcolor=(1, 1, 1))
-            if self.show_exact and self.pde.has_exact():
-                mlab.surf(xn, yn, self.pde.exact(xn, yn), colormap="viridis", representation="wireframe")
-            self.plt1 = mlab.surf(xn, yn, pn, colormap="viridis", opacity=0.8)
-            mlab.colorbar(self.plt1)
-        else:
-            self.plt1.mlab_source.scalars = pn
-        return self.get_error(xn, yn, pn)
-
-    def plot_weights(self):
-        from mayavi import mlab
-        x, y = (t.detach().cpu().numpy() for t in self.nn.centers())
-        h = self.nn.widths().detach().cpu().numpy()
-        if not self.plt2:
-            self.plt2 = mlab.points3d(x, y, np.zeros_like(x), h, mode="2dcircle", scale_factor=1.0,
-                                      color=(1, 0, 0), opacity=0.6)
-        else:
-            self.plt2.mlab_source.trait_set(x=x, y=y, scalars=h)
-
+    # live plotting is not provided (the reference's mayavi code, spinn2d.py:45-94, is visualisation)
     def plot(self):
-        from mayavi import mlab
-        err = self.plot_solution()
-        self.plot_weights()
-        mlab.process_ui_events()
-        return err
+        raise NotImplementedError(NO_LIVE_PLOT)
 
-    def show(self):
-        from mayavi import mlab
-        mlab.show()
+    plot_solution = plot_weights = plot
 
 
 class App2D(App):

@@ -319,3 +319,21 @@ void hc_s2_bwd(int mask, int N, int M, const float* x, const float* y, const flo
 }
 
 }  // extern "C"
+
+// ---- residual epilogues of the problem scripts (ode3 forcing, cavity point residual + dLoss/dJets) ----
+extern "C" {
+void hc_ode3_forcing(int n, const float* x, float Kc, float* f) {
+  for (int i = 0; i < n; ++i) f[i] = ode3_forcing(x[i], Kc);
+}
+// J, g: [5][n][3]; loss: [n]
+void hc_cavity_residual(int n, const float* J, float nu, float* g, float* loss) {
+  for (int i = 0; i < n; ++i) {
+    float Jp[5][3], gp[5][3];
+    for (int a = 0; a < 5; ++a)
+      for (int k = 0; k < 3; ++k) Jp[a][k] = J[((size_t)a * n + i) * 3 + k];
+    loss[i] = cavity_residual_point(Jp, nu, gp);
+    for (int a = 0; a < 5; ++a)
+      for (int k = 0; k < 3; ++k) g[((size_t)a * n + i) * 3 + k] = gp[a][k];
+  }
+}
+}  // extern "C"

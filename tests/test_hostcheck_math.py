@@ -251,3 +251,32 @@ def test_fast_softplus_far_field_and_extreme_offsets(hc):
     for got, key in ((dc, "d_xc"), (dd, "d_yc"), (dh, "d_h"), (dW, "d_W")):
         assert np.isfinite(got).all()
         assert mixed_err(got, np.asarray(G[key]).reshape(-1)) < TOL, key
+
+
+# ---- residual epilogues (ode3 forcing, cavity residual and its jet gradients) -----------------
+def test_ode3_forcing_matches_the_script_formula(hc):
+    x = f32(np.linspace(0.0, 1.0, 301))
+    f = np.zeros_like(x)
+    hc.hc_ode3_forcing(x.size, _ptr(x), ctypes.c_float(0.01), _ptr(f))
+    K, xd = 0.01, x.astype(np.float64)
+    ref = -(K * (-6 * xd + 4 / 3.) + xd * (2 * xd - 2. / 3) ** 2) * np.exp(-(xd - 1 / 3.) ** 2 / K) / K ** 2   # ode3.py:13-15
+    assert np.max(np.abs(f - ref)) < 3e-6 * np.max(np.abs(ref))
+
+
+def test_cavity_residual_gradients_match_autograd(hc):
+    import torch
+    n = 97
+    rs = np.random.RandomState(9)
+    J = f32(rs.randn(5, n, 3))
+    g, loss = np.zeros_like(J), np.zeros(n, np.float32)
+    hc.hc_cavity_residual(n, _ptr(J), ctypes.c_float(0.01), _ptr(g), _ptr(loss))
+    Jt = torch.tensor(J, dtype=torch.float64, requires_grad=True)
+    u, v = Jt[0, :, 0], Jt[0, :, 1]
+    ux, vx, px = Jt[1, :, 0], Jt[1, :, 1], Jt[1, :, 2]
+    uy, vy, py = Jt[2, :, 0], Jt[2, :, 1], Jt[2, :, 2]
+    nu = 0.01                                                                 # cavity.py:94-100
+    per_point = (ux + vy) ** 2 + (u * ux + v * uy + px - nu * (Jt[3, :, 0] + Jt[4, :, 0])) ** 2 \
+        + (u * vx + v * vy + py - nu * (Jt[3, :, 1] + Jt[4, :, 1])) ** 2
+    per_point.sum().backward()
+    assert np.max(np.abs(loss - per_point.detach().numpy())) < 1e-5 * per_point.max().item()
+    assert np.max(np.abs(g - Jt.grad.numpy())) < 1e-5 * np.abs(Jt.grad.numpy()).max()
