@@ -44,7 +44,7 @@ KERNEL_COST = {
     ("gaussian", "fwd"): dict(flop=23.0, instr=14, mufu=1),
     ("gaussian", "bwd_structured"): dict(flop=25.0, instr=16, mufu=1),
     ("gaussian", "bwd_general"): dict(flop=53.0, instr=32, mufu=1),
-    ("softplus", "fwd"): dict(flop=42.0, instr=30, mufu=5),
+    ("softplus", "fwd"): dict(flop=49.0, instr=34, mufu=5),
     ("softplus", "bwd_structured"): dict(flop=74.0, instr=51, mufu=4),
     ("softplus", "bwd_general"): dict(flop=95.0, instr=63, mufu=5),
 }
@@ -708,7 +708,7 @@ def run_ours(args):
             softplus = {"value": N * M / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
                         "loss": float(sstep.pack.view("loss")[0]), "kernels": {"fwd": sf, "bwd": sb},
                         "what": "the same fused interior step with the softplus-hat kernel (spinn2d.py:195-205): "
-                                "s2k1_fwd_kernel is MUFU-bound (5 MUFU + 30 FP32 slots per pair), s2k1_bwd_kernel "
+                                "s2k1_fwd_kernel is MUFU-bound (5 MUFU + 34 FP32 slots per pair), s2k1_bwd_kernel "
                                 "FP32-bound (51 slots + 4 MUFU); reference CPU rate for this kernel: 4.4e6 evals/s "
                                 "on 8 threads (BASELINE.md section 2)"}
             del sstep, pde_s, nn_s

@@ -394,8 +394,7 @@ SP_HD void g2_bwd_finish_m(float h, float W, const float* a, float* dW, float* d
 // factor q^-1 = EK^-1/4 so that R = 1/(A_x' A_y') squares to EK/(A_x A_y)^2 without an extra multiply.
 // The series branches of the generic path (log1p / 1-e for small arguments) are not needed at the
 // level of the SUMS over nodes / points: their absolute errors (~1e-7 of the largest term) are
-// those of fp32 rounding; s2_log2_1pw adds the first-order correction of the rounding of 1+w (what
-// is left in u is MUFU.LG2's own absolute error, 2^-22.6 per node).
+// those of fp32 rounding; the one exception is log1p at small w (s2_log2_1pw).
 // =============================================================================
 constexpr float HAT_Q_F    = 2.568050838266732f;       // EK2^(1/4)
 constexpr float HAT_IQ_F   = 0.3894003907940293f;      // 1/q
@@ -440,13 +439,18 @@ SP_HD S2Head s2_head(float2 x2, float2 y2, float2 nc, float2 nd, float2 c1) {
   return h;
 }
 
-// log2(1+w) from MUFU.LG2 of the ROUNDED sum u = fl(1+w), plus the first-order correction for that
-// rounding: ln(1+w) = ln u + (w - (u-1))/u  (u-1 and w-(u-1) are exact in fp32; 1/u = i is at hand).
-// 4 packed instructions; on the MUFU-bound forward they ride in spare FP32 slots.
+// log2(1+w).  MUFU.LG2 has an ABSOLUTE error (~2^-23 near 1) that does not shrink with w, and at
+// BASELINE density a few hundred nodes with small w contribute to every point: for w < 1/32 the
+// 4-term series of log1p (error w^5/5 < 6e-9) is taken instead -- per lane select, 4 packed
+// instructions that ride in spare FP32 slots of the MUFU-bound forward.
 SP_HD float2 s2_log2_1pw(const S2Head& h) {
-  const float2 um1 = f2add(h.opw, f2dup(-1.0f));
-  const float2 d = f2fma(um1, f2dup(-1.0f), h.w);
-  return f2fma(f2mul(d, h.i), f2dup(LOG2E_F), f2lg2(h.opw));
+  const float L1 = LOG2E_F, L2 = -0.5f * LOG2E_F, L3 = LOG2E_F / 3.0f, L4 = -0.25f * LOG2E_F;
+  float2 p = f2fma(h.w, f2dup(L4), f2dup(L3));
+  p = f2fma(h.w, p, f2dup(L2));
+  p = f2fma(h.w, p, f2dup(L1));
+  p = f2mul(h.w, p);
+  const float2 lg = f2lg2(h.opw);
+  return make_float2(h.w.x < 0.03125f ? p.x : lg.x, h.w.y < 0.03125f ? p.y : lg.y);
 }
 
 // acc: u, ux, uy, uxx, uyy (, uxy); lanes = partial sums over one node parity

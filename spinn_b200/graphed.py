@@ -102,6 +102,8 @@ class GraphedOptimizer(DistributedOptimizer):
             if stop:
                 break
         self.loss = self.loss[:done_before] + loss_buf[:i].tolist()
+        if hasattr(self.pde, "disable_static_sampling"):
+            self.pde.disable_static_sampling()
         self.time_taken = time.perf_counter() - t0
         print(f"Done. Took {self.time_taken:.3f} seconds.")
         if self.plot:

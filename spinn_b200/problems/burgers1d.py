@@ -3,7 +3,10 @@
 
     python -m spinn_b200.problems.burgers1d --gpu
 """
+import os
+
 import numpy as np
+import torch
 
 from ..common import add_flags, tensor
 from ..spinn2d import App2D, Plotter2D, SPINN2D
@@ -21,6 +24,18 @@ def initial_profile(ic, x, t, a=0.0):
     shift, freq = (0.75, 1.0) if ic == "sin" else (0.5, 2.0)
     z = x - a * t + shift
     return (np.heaviside(z, 0.5) - np.heaviside(z - 1.0, 0.5)) * np.sin(z * np.pi * freq)
+
+
+class MyPlotter(Plotter2D):
+    """results.npz of the reference's burgers plotter (burgers1d.py:46-60): the field on a fixed
+    500 x 11 grid of (x, t) in [-1,1] x [0,1] (keys x, t, u) next to the plot-grid data (xp, tp, up);
+    there is no exact solution, so no u_exact entry."""
+
+    def save(self, dirname):
+        torch.save(self.nn.state_dict(), os.path.join(dirname, "model.pt"))
+        x, t = np.mgrid[-1:1:500j, 0:1:11j]
+        xp, tp, up = self.get_plot_data()
+        np.savez(os.path.join(dirname, "results.npz"), x=x, t=t, u=self.field_on_grid(x, t), xp=xp, tp=tp, up=up)
 
 
 class Burgers1D(IBVP2D):
@@ -67,7 +82,7 @@ DEFAULTS = dict(nodes=200, samples=1000, xL=-1.0, xR=1.0, lr=1e-3)
 
 
 def make_app():
-    return App2D(pde_cls=Burgers1D, nn_cls=SPINN2D, plotter_cls=Plotter2D)
+    return App2D(pde_cls=Burgers1D, nn_cls=SPINN2D, plotter_cls=MyPlotter)
 
 
 if __name__ == "__main__":

@@ -34,6 +34,8 @@ class IBVP2D(SubSampling, PDE):
     def _compute_derivatives(self, u, xs, ts):
         return derivs.jets_2d(u, xs, ts)
 
+    _compute_derivatives.drops_mixed_derivative = True      # the recipe this class's flag vouches for
+
     @staticmethod
     def _get_points_split(L, T, n):
         size = np.sqrt(L * T / n)                                     # ibvp2d_base.py:83-87

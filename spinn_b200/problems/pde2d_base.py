@@ -45,6 +45,8 @@ class RegularPDE(SubSampling, PDE):
     def _compute_derivatives(self, u, xs, ys):
         return derivs.jets_2d(u, xs, ys)
 
+    _compute_derivatives.drops_mixed_derivative = True      # the recipe this class's flag vouches for
+
     def __init__(self, n_nodes, ns, nb=None, nbs=None, sample_frac=1.0):
         self.sample_frac = sample_frac
         # free nodes: n x n cell-centred grid (pde2d_base.py:66-74)

@@ -59,6 +59,8 @@ class Poisson2D(SubSampling, PDE):
     def _compute_derivatives(self, u, xs, ys):
         return derivs.jets_2d(u, xs, ys)
 
+    _compute_derivatives.drops_mixed_derivative = True      # the recipe this class's flag vouches for
+
     def __init__(self, f_nodes_int, f_nodes_bdy, f_samples_int, f_samples_bdy, sample_frac=1.0):
         self.f_nodes_int, self.f_nodes_bdy = f_nodes_int, f_nodes_bdy
         self.f_samples_int, self.f_samples_bdy = f_samples_int, f_samples_bdy

@@ -13,6 +13,7 @@ class SubSampling:
     """Expects `sample_frac`, `rng_interior`, `sample_size` on the instance."""
 
     _idx_dev = None
+    _idx_live = False          # True only while a graphed solve() is replaying against _idx_dev
 
     def uses_all_samples(self):
         return abs(self.sample_frac - 1.0) < 1e-3
@@ -21,7 +22,7 @@ class SubSampling:
         """None = all points; otherwise an index (NumPy array, or the static device buffer)."""
         if self.uses_all_samples():
             return None
-        if self._idx_dev is not None:
+        if self._idx_dev is not None and self._idx_live:
             return self._idx_dev
         return np.random.choice(self.rng_interior, size=self.sample_size, replace=False)
 
@@ -34,7 +35,10 @@ class SubSampling:
         raise NotImplementedError()
 
     def enable_static_sampling(self):
-        if self.uses_all_samples() or self._idx_dev is not None:
+        if self.uses_all_samples():
+            return
+        self._idx_live = True
+        if self._idx_dev is not None:          # a later graphed solve(): the captured step reads this buffer
             return
         import torch
         # ring of pinned staging buffers: the host runs ahead of the GPU in graph mode, so a
@@ -44,8 +48,13 @@ class SubSampling:
         self._idx_turn = 0
         self._idx_dev = torch.zeros(self.sample_size, dtype=torch.int64, device=self._sampling_device())
 
+    def disable_static_sampling(self):
+        """After a graphed solve(): eager calls of interior() draw fresh indices again (the static
+        buffer is kept for the next replay)."""
+        self._idx_live = False
+
     def graph_pre_step(self):
-        if self._idx_dev is None:
+        if self._idx_dev is None or not self._idx_live:
             return
         import torch
         idx = np.random.choice(self.rng_interior, size=self.sample_size, replace=False)

@@ -125,7 +125,12 @@ class SPINN2D(nn.Module):
         self.activation = activation
         self.kind = kernel_kind(activation)
         self.use_pu = use_pu
-        self.mixed_derivative = bool(getattr(pde, "needs_mixed_derivative", True))
+        # u_xy is skipped only if the problem class says so AND still uses the packaged derivative
+        # recipe the statement was made for: a subclass that overrides `_compute_derivatives`
+        # (e.g. to use u_xy) gets the complete tower again instead of a silently zero mixed term
+        recipe = getattr(type(pde), "_compute_derivatives", None)
+        vouched = getattr(recipe, "drops_mixed_derivative", False)
+        self.mixed_derivative = not (getattr(pde, "needs_mixed_derivative", True) is False and vouched)
         self.layer1 = Shift2D(pde.nodes(), pde.fixed_nodes(), fixed_h=fixed_h)
         self.layer2 = nn.Linear(self.layer1.n, pde.n_vars(), bias=not use_pu)
         self.layer2.weight.data.fill_(0.0)
@@ -198,7 +203,16 @@ class Plotter2D(Plotter):
     def save(self, dirname):
         torch.save(self.nn.state_dict(), os.path.join(dirname, "model.pt"))
         x, y, u = self.get_plot_data()
-        np.savez(os.path.join(dirname, "results.npz"), x=x, y=y, u=u, u_exact=self.pde.exact(x, y))
+        fields = dict(x=x, y=y, u=u)
+        exact = self.pde.exact(x, y) if self.pde.has_exact() else None
+        if exact is not None:                    # no pickled `None` entry for problems without an exact solution
+            fields["u_exact"] = exact
+        np.savez(os.path.join(dirname, "results.npz"), **fields)
+
+    def field_on_grid(self, x, t):
+        """u evaluated on a NumPy grid (level-0 call of the fused forward), shaped like the grid."""
+        u = self.nn(tensor(x.ravel()), tensor(t.ravel())).detach().cpu().numpy()
+        return u.reshape(x.shape)
 
     def get_plot_data(self):
         x, y = self.pde.plot_points()
