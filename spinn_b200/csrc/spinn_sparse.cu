@@ -13,6 +13,7 @@
 //   * nodes are visited through `node_perm` (e.g. Morton order of the centres);
 //   * consecutive points should be close in space (regular grids are; clouds can be sorted once).
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -39,6 +40,11 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
     char _b[400];                                           \
     snprintf(_b, sizeof(_b), __VA_ARGS__);                  \
     return spinn_fail_msg(code, _b);                        \
+  } while (0)
+#define SP_CUDA(expr)                                                                \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) SP_FAIL(SPINN_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 #define SP_LAUNCH_CHECK(name)                                                        \
   do {                                                                               \
@@ -486,7 +492,7 @@ SparsePlan plan(int N, int M) {
   off = 0;
   p.off_pts = off;  off += align_up((size_t)4 * p.N2 * sizeof(float4), 256);
   p.off_sbb = off;  off += align_up((size_t)(p.nsub > 0 ? p.nsub : 1) * sizeof(float4), 256);
-  p.off_part = off; off += align_up((size_t)1024 * 4 * p.Mp * sizeof(float), 256);
+  p.off_part = off; off += align_up((size_t)p.chunks * 4 * p.Mp * sizeof(float), 256);
   p.off_bias = off; off += align_up((size_t)BIAS_BLOCKS_S * sizeof(float), 256);
   p.off_htmp = off; off += align_up((size_t)p.Mp * sizeof(float), 256);
   p.bwd_bytes = off;
@@ -544,13 +550,19 @@ int spinn2d_jets_fwd_sparse(int kind, int level, int N, int M_free, int M_fixed,
   if (blocks > cap) blocks = cap;
   if (level == 3) {
     auto kfn = g2k1_fwd_sparse_kernel<true>;
-    static bool configured[64] = {false};
-    if (!configured[cur_dev]) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured[cur_dev] = true; }
+    static std::atomic<int> configured[64];
+    if (configured[cur_dev].load(std::memory_order_acquire) == 0) {
+      SP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT));
+      configured[cur_dev].store(1, std::memory_order_release);
+    }
     kfn<<<(int)blocks, FWD_T, p.fwd_smem, s>>>(N, x, y, recs, bb, r2, p.nblk, bias, jets, vec_ok, stats);
   } else {
     auto kfn = g2k1_fwd_sparse_kernel<false>;
-    static bool configured[64] = {false};
-    if (!configured[cur_dev]) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT); configured[cur_dev] = true; }
+    static std::atomic<int> configured[64];
+    if (configured[cur_dev].load(std::memory_order_acquire) == 0) {
+      SP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_LIMIT));
+      configured[cur_dev].store(1, std::memory_order_release);
+    }
     kfn<<<(int)blocks, FWD_T, p.fwd_smem, s>>>(N, x, y, recs, bb, r2, p.nblk, bias, jets, vec_ok, stats);
   }
   SP_LAUNCH_CHECK("g2k1_fwd_sparse_kernel");
@@ -575,10 +587,13 @@ int spinn2d_jets_bwd_sparse(int kind, int level, int present_mask, int N, int M_
   const int mask = present_mask == 0 ? all : (present_mask & all);
   cudaStream_t s = (cudaStream_t)stream;
   if (N == 0 || mask == 0) {
-    if (M_free) { cudaMemsetAsync(d_xc, 0, sizeof(float) * M_free, s); cudaMemsetAsync(d_yc, 0, sizeof(float) * M_free, s); }
-    cudaMemsetAsync(d_h, 0, sizeof(float) * (h_is_scalar ? 1 : M), s);
-    cudaMemsetAsync(d_W, 0, sizeof(float) * M, s);
-    if (d_bias) cudaMemsetAsync(d_bias, 0, sizeof(float), s);
+    if (M_free) {
+      SP_CUDA(cudaMemsetAsync(d_xc, 0, sizeof(float) * M_free, s));
+      SP_CUDA(cudaMemsetAsync(d_yc, 0, sizeof(float) * M_free, s));
+    }
+    SP_CUDA(cudaMemsetAsync(d_h, 0, sizeof(float) * (h_is_scalar ? 1 : M), s));
+    SP_CUDA(cudaMemsetAsync(d_W, 0, sizeof(float) * M, s));
+    if (d_bias) SP_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float), s));
     return SPINN_OK;
   }
   if (!x || !y || !gjets) SP_FAIL(SPINN_E_BADARG, "null point/gradient pointer in jets_bwd_sparse");

@@ -122,6 +122,21 @@ class CudaBackend:
 
 
     # ---- compact-support variants (2-D Gaussian, K=1); see include/spinn_b200.h -------------
+    _ws_cache = {}
+
+    def _sparse_ws(self, nbytes, dev):
+        """Backward workspace of the compact-support path, cached per (size, device, stream): it holds
+        per-chunk partial sums (MBs at M=4096) and used to be allocated on every backward call."""
+        if torch.cuda.is_current_stream_capturing():       # graph capture: memory must come from the graph's pool
+            return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        key = (nbytes, dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            if len(self._ws_cache) > 8:
+                self._ws_cache.clear()
+            ws = self._ws_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return ws
+
     def forward_sparse(self, level, x, y, xf, yf, xfix, yfix, h, W, b, perm, cutoff, stats=None):
         lib = _cabi.load()
         dev = self._check(x, y, xf, yf, xfix, yfix, h, W, b)
@@ -153,7 +168,7 @@ class CudaBackend:
             d_W = torch.empty((1, M), dtype=torch.float32, device=dev)
             d_b = torch.empty(1, dtype=torch.float32, device=dev) if want_bias else None
             nbytes = lib.spinn2d_sparse_bwd_workspace_bytes(N, M)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = self._sparse_ws(nbytes, dev)
             rc = lib.spinn2d_jets_bwd_sparse(GAUSSIAN, level, mask, N, Mf, Mx, 1, _ptr(x), _ptr(y), _ptr(xf),
                                              _ptr(yf), _ptr(xfix), _ptr(yfix), _ptr(h), int(h.numel() == 1),
                                              _ptr(W), _ptr(gj), _ptr(perm), float(cutoff), _ptr(d_xc),
