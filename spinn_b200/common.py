@@ -198,6 +198,15 @@ class Optimizer:
         self.opt = None
         self.loss_for_tolerance = False
 
+    def make_optimizer(self):
+        """`opt_class(nn.parameters(), lr=lr)` as the reference (common.py:255); Adam on CUDA parameters
+        is asked for its single multi-tensor kernel (`fused=True`: same update rule, one launch instead
+        of ~10 per step -- the small configs are launch-bound)."""
+        params = list(self.nn.parameters())
+        if self.opt_class is torch.optim.Adam and params and all(p.is_cuda for p in params):
+            return torch.optim.Adam(params, lr=self.lr, fused=True)
+        return self.opt_class(params, lr=self.lr)
+
     def use_loss_for_tolerance(self):
         self.loss_for_tolerance = True
 
@@ -225,7 +234,7 @@ class Optimizer:
 
     def solve(self):
         if self.opt is None:
-            self.opt = self.opt_class(self.nn.parameters(), lr=self.lr)
+            self.opt = self.make_optimizer()
         if self.plot:
             self.plotter.plot()
         t0 = time.perf_counter()

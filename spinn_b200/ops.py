@@ -235,9 +235,19 @@ class _FusedJets(torch.autograd.Function):
         # rows of absent jets are never read by the kernels (present-mask): no zero fill
         gj = torch.empty((ng, N, K), dtype=torch.float32, device=x.device)
         mask = 0
-        for i in present:
-            gj[i].copy_(gs[i].reshape(N, K))
-            mask |= 1 << i
+        i = 0
+        while i < len(present):                  # one copy kernel per RUN of adjacent present rows
+            j = i
+            while j + 1 < len(present) and present[j + 1] == present[j] + 1:
+                j += 1
+            rows = [gs[r].reshape(N, K) for r in present[i:j + 1]]
+            if len(rows) == 1:
+                gj[present[i]].copy_(rows[0])
+            else:
+                torch.stack(rows, 0, out=gj[present[i]:present[j] + 1])
+            for r in present[i:j + 1]:
+                mask |= 1 << r
+            i = j + 1
         if ctx.sparse is not None and lv <= 2:
             cutoff, perm = ctx.sparse
             d_xc, d_yc, d_h, d_W, d_b = _BACKEND.backward_sparse(
@@ -283,6 +293,17 @@ def morton_order(xc, yc):
     return torch.argsort(code).to(torch.int32)
 
 
+_ZEROS = {}
+
+
+def _zero_scalar(like):
+    key = (like.device, like.dtype)
+    z = _ZEROS.get(key)
+    if z is None:
+        z = _ZEROS[key] = torch.zeros((), device=like.device, dtype=like.dtype)
+    return z
+
+
 class _Attach(torch.autograd.Function):
     """out = v, but with DECLARED derivatives d out/dx = vx, d out/dy = vy.
 
@@ -302,8 +323,8 @@ class _Attach(torch.autograd.Function):
         vx, vy = ctx.saved_tensors
 
         def along(v):                # sum_k g * v; a derivative declared "not provided" reads as zero
-            if v is None:            # (a broadcast scalar zero: no fill kernel over N elements)
-                return g.new_zeros(()).expand(g.shape[0])
+            if v is None:            # (a cached scalar zero, broadcast: no kernel at all)
+                return _zero_scalar(g).expand(g.shape[0])
             t = g * v
             if t.dim() == 1:
                 return t
