@@ -424,14 +424,6 @@ def run_ours(args):
         out_host = torch.empty(pack.flat.numel(), dtype=torch.float32).pin_memory()
         params = [l1.x, l1.y, l1.h, l2.weight, l2.bias]
 
-        def bind_grads():
-            """The parameters' .grad are VIEWS of the packed [grads|loss] buffer (as
-            dist_optimizer.DistributedOptimizer does): autograd accumulates in place, no pack copies."""
-            l1.x.grad, l1.y.grad = pack.view("d_x"), pack.view("d_y")
-            l1.h.grad = pack.view("d_h").view_as(l1.h)
-            l2.weight.grad = pack.view("d_W").view_as(l2.weight)
-            l2.bias.grad = pack.view("d_b")
-
         # Host->device copies run on a side stream, one step ahead (what a data loader does);
         # every step still uploads its own inputs and downloads its own result inside the
         # timed region.
@@ -456,14 +448,20 @@ def run_ours(args):
             upload()                                                   # inputs of the following step
             x.requires_grad_(True)
             y.requires_grad_(True)
-            flat = pack.flat
-            flat.zero_()
-            bind_grads()                                               # .grad = views of the packed buffer
+            for p_ in params:
+                p_.grad = None
             u = nn(x, y)                                               # public plug-in call
             u, ux, uy, uxx, uyy = pde._compute_derivatives(u, x, y)    # the problem class's ag.grad recipe
             res = pde.pde(x, y, u, ux, uy, uxx, uyy)
             lossv = (res ** 2).sum() / N
-            lossv.backward()                                           # accumulates in place into the views
+            lossv.backward()
+            flat = pack.flat
+            flat.zero_()
+            pack.view("d_x").copy_(l1.x.grad)
+            pack.view("d_y").copy_(l1.y.grad)
+            pack.view("d_h").copy_(l1.h.grad.reshape(-1))
+            pack.view("d_W").copy_(l2.weight.grad.reshape(-1))
+            pack.view("d_b").copy_(l2.bias.grad)
             pack.view("loss").copy_(lossv.detach().reshape(1))
             pack.all_reduce()
             out_host.copy_(flat, non_blocking=True)
@@ -487,13 +485,20 @@ def run_ours(args):
         # still uploads its inputs from pinned host memory (prefetched into the OTHER static
         # buffer on the copy stream), replays, downloads the packed result and synchronises.
         def body(x, y):
-            pack.flat.zero_()
-            bind_grads()
+            for p_ in params:
+                p_.grad = None
             u = nn(x, y)
             u, ux, uy, uxx, uyy = pde._compute_derivatives(u, x, y)
             res = pde.pde(x, y, u, ux, uy, uxx, uyy)
             lossv = (res ** 2).sum() / N
             lossv.backward(inputs=params)
+            flat = pack.flat
+            flat.zero_()
+            pack.view("d_x").copy_(l1.x.grad)
+            pack.view("d_y").copy_(l1.y.grad)
+            pack.view("d_h").copy_(l1.h.grad.reshape(-1))
+            pack.view("d_W").copy_(l2.weight.grad.reshape(-1))
+            pack.view("d_b").copy_(l2.bias.grad)
             pack.view("loss").copy_(lossv.detach().reshape(1))
             pack.all_reduce()
 

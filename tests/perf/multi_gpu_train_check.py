@@ -37,7 +37,14 @@ for extra in ([], ["--graph"]):
               f"{1e3 * dt / steps:.3f} ms/step incl. setup", flush=True)
     assert rel[:10].max() < 5e-5 and rel.max() < 3e-3, (extra, rel.max())
 if rank == 0:
-    print("OK")
+    print("OK", flush=True)
+# explicit teardown: with a captured NCCL all-reduce alive, interpreter exit without it left the NCCL
+# watchdog stuck (B200 x2, torch 2.11 / NCCL 2.28) -- run this script under `timeout`
+import torch.distributed as dist  # noqa: E402
+del app
+torch.cuda.synchronize()
+if dist.is_initialized():
+    dist.destroy_process_group()
 import torch.distributed as dist
 if dist.is_initialized():
     dist.destroy_process_group()
