@@ -203,7 +203,8 @@ class Optimizer:
         is asked for its single multi-tensor kernel (`fused=True`: same update rule, one launch instead
         of ~10 per step -- the small configs are launch-bound)."""
         params = list(self.nn.parameters())
-        if self.opt_class is torch.optim.Adam and params and all(p.is_cuda for p in params):
+        if self.opt_class is torch.optim.Adam and params and all(
+                p.is_cuda and p.dim() > 0 and p.dtype == torch.float32 for p in params):
             return torch.optim.Adam(params, lr=self.lr, fused=True)
         return self.opt_class(params, lr=self.lr)
 
