@@ -816,8 +816,9 @@ def run_ours(args):
                                 "structured: this residual has upstream gradients for u_xx,u_yy only (what "
                                 "autograd hands the op through the plug-in API too); every pair evaluated; "
                                 "see general_upstream for the 5-row variant"),
-                   "l2_policy": "inputs larger than L2: per step x,y 8 B + jets 20 B + gjets 20 B + packed "
-                                "point records 32 B per point (>300 MB at 4M points vs 126 MB L2)",
+                   "l2_policy": "inputs larger than L2: per step and point x,y 8 B (read by the forward and its "
+                                "epilogue), jets 20 B written, packed point records 32 B written + 32 B read "
+                                "(>400 MB at 4M points vs 126 MB L2)",
                    "collective": "one NCCL all_reduce(sum) of the packed [grads|loss] vector per step"
                                  if ws > 1 else "none (1 GPU)"},
         "loss": loss, "train_step_ms": (train_step or {}).get("ms", ms_step), "train_step": train_step,
