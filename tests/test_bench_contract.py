@@ -47,3 +47,20 @@ def test_our_arm_has_no_cpu_fallback():
         pytest.skip("a GPU is present")
     r = _run(["--steps", "1", "--warmup", "0"])
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_roofline_helpers_read_the_committed_ncu_capture():
+    """roofline.traffic comes from the committed `ncu --set full` capture of the BASELINE workload
+    (profiles/r02_ncu_kernels.json, tools/ncu_summary.py json), never from a source constant; the
+    per-kernel report turns a duration into fractions of the nominal FP32 / MUFU pipes."""
+    sys.path.insert(0, ROOT)
+    import bench
+    t = bench.ncu_traffic("g2k1_bwd_kernel", 4194304, 4096)
+    assert t is not None and t["kernel"].startswith("g2k1_bwd_kernel<4, 256, 2, 256, 1>")
+    assert 1.3e8 < t["bytes"] < 1.6e8                      # algorithmic: 134 MB of point records + partials
+    assert bench.ncu_traffic("g2k1_bwd_kernel", 1048576, 4096) is None      # other workloads: no number
+    r = bench.kernel_report("gaussian", "bwd_structured", 4194304.0 * 4096, 9.4074, 1965.0)
+    assert abs(r["frac"] - 0.6132) < 1e-3 and abs(r["fp32_slot_frac"] - 0.7849) < 1e-3
+    assert abs(r["mufu_frac"] - 0.3925) < 1e-3 and r["binding_pipe"] == "fp32"
+    s = bench.kernel_report("softplus", "fwd", 4194304.0 * 4096, 21.0817, 1965.0)
+    assert s["binding_pipe"] == "mufu" and abs(s["binding_pipe_frac"] - 0.8757) < 1e-3
